@@ -1,0 +1,194 @@
+/*
+ * mapeval_b200.h — C-ABI of libmapeval_b200.so
+ *
+ * B200-native (sm_100a) replacement for the metric hot path of MapEval
+ * (JokerJohn/Cloud_Map_Evaluation).  The reference has no FFI of its own: the
+ * path sits behind C++ member functions of `class MapEval` that talk through
+ * member state (map_eval/src/map_eval.h:121-362).  Each entry point below names
+ * the reference member function(s) it replaces (paths relative to the reference
+ * root, `map_eval/src/`).  Plain C: pointers, sizes, PODs.  No C++/torch types.
+ *
+ * Conventions
+ *   - every function returns ME_OK (0) or a negative me_status; after an error
+ *     me_last_error(ctx) holds a message (the reference's convention is the
+ *     0 / -1 return of MapEval::process(), map_eval.cpp:16,28,34,101).
+ *   - clouds are N x 3 fp64, array-of-structs — the layout of Open3D's
+ *     `std::vector<Eigen::Vector3d> points_` that the reference reads.
+ *   - one me_ctx = one GPU = one caller thread at a time.  Multi-GPU = one
+ *     context per process/GPU with {rank, world} set; the *_accum entry points
+ *     return sum-reducible partial accumulators for this rank's query range,
+ *     the caller all-reduces them (NCCL) and calls the host-side *_finalize.
+ *   - there is NO CPU fallback in this library: without a usable CUDA device
+ *     me_create fails with ME_ERR_NO_DEVICE.
+ */
+#ifndef MAPEVAL_B200_H_
+#define MAPEVAL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ME_ABI_VERSION 1
+
+typedef enum {
+  ME_OK = 0,
+  ME_ERR_INVALID = -1,     /* bad argument / call order                       */
+  ME_ERR_NO_DEVICE = -2,   /* no CUDA device / wrong architecture             */
+  ME_ERR_CUDA = -3,        /* a CUDA runtime call failed (see me_last_error)  */
+  ME_ERR_NOMEM = -4,       /* device or host allocation failed                */
+  ME_ERR_EMPTY = -5,       /* a required cloud is empty (map_eval.cpp:32-35)  */
+  ME_ERR_RANGE = -6        /* coordinates / voxel indices outside what the grids can index */
+} me_status;
+
+enum { ME_CLOUD_EST = 0, ME_CLOUD_GT = 1 };
+
+/* kept-pair cut-off of the 1-NN sweep */
+enum {
+  ME_CUTOFF_SQDIST_LE_R = 0,  /* keep iff d2 <= icp_max_distance  (path A as written, map_eval.cpp:1219,1232) */
+  ME_CUTOFF_DIST_LT_R = 1     /* keep iff d2 <  icp_max_distance^2 (Open3D EvaluateRegistration, map_eval.cpp:1168) */
+};
+
+/* how the gt->est pairs are looked up by the accumulator pass */
+enum {
+  ME_PAIRING_AS_WRITTEN = 0,  /* map_eval.cpp:1233 stores (nn_est, i_gt) but :1241 passes (source=gt,target=est),
+                                 so :1093-1094 reads gt[nn_est] and est[i_gt]; reproduced verbatim.  Pairs whose
+                                 swapped indices fall outside the clouds (undefined behaviour in the reference)
+                                 are dropped and counted in n_ub. */
+  ME_PAIRING_GEOMETRIC = 1    /* distance between the gt point and its nearest est point */
+};
+
+typedef struct me_ctx me_ctx;
+
+typedef struct {
+  int32_t abi_version;     /* must be ME_ABI_VERSION                                       */
+  int32_t device;          /* CUDA device ordinal                                          */
+  int32_t rank, world;     /* this context evaluates queries [rank*N/world,(rank+1)*N/world) */
+  void   *stream;          /* cudaStream_t to launch on; NULL = library-owned stream       */
+  double  nn_cell_size;    /* edge of the hashed-grid cells in metres; <= 0 = auto         */
+  int64_t max_grid_cells;  /* budget for the dense cell table; <= 0 = default (2^28)       */
+} me_options;
+
+/* ---- a1/a2/a4: AC / COM / CD inlier statistics and full Chamfer ------------------------------- */
+
+typedef struct {
+  double  tau[5];            /* accuracy_level / trunc_dist_ (map_eval.h:85)               */
+  double  icp_max_distance;  /* R (map_eval.h:69)                                          */
+  int32_t cutoff_mode;       /* ME_CUTOFF_*                                                */
+  int32_t pairing;           /* ME_PAIRING_* (gt->est direction only)                      */
+  int32_t want_full_cd;      /* also accumulate sum sqrt(d2) over ALL queries (map_eval.cpp:1398-1431) */
+  int32_t directions;        /* bit0: est->gt, bit1: gt->est; 0 = both                     */
+} me_nn_params;
+
+/* sum-reducible partial accumulators of one direction (int64 block first, then fp64 block) */
+#define ME_NN_ACCUM_I64 9
+#define ME_NN_ACCUM_F64 13
+typedef struct {
+  int64_t n_query;           /* queries evaluated by this rank                             */
+  int64_t n_corr;            /* kept pairs |C|                                             */
+  int64_t n_inlier[5];       /* pairs with d <= tau_k (number_vec, map_eval.cpp:1099-1123) */
+  int64_t n_ub;              /* ME_PAIRING_AS_WRITTEN: dropped out-of-range pairs          */
+  int64_t n_far;             /* queries resolved by the far (ring-expansion) kernel        */
+  double  sum_d[5];          /* sum of d   over pairs with d <= tau_k (mean_vec)           */
+  double  sum_d2[5];         /* sum of d^2 over pairs with d <= tau_k (rmse_vec)           */
+  double  sum_d_all;         /* sum of d   over all kept pairs  (sigma closed form)        */
+  double  sum_d2_all;        /* sum of d^2 over all kept pairs                             */
+  double  sum_nn_dist;       /* sum of sqrt(d2_nn) over ALL queries (full CD)              */
+} me_nn_accum;
+
+typedef struct {             /* == est_gt_results / gt_est_results (map_eval.cpp:1140-1144) */
+  int64_t n_source, n_corr;
+  int64_t n_inlier[5];
+  int64_t n_ub;
+  double  mean[5], rmse[5], fitness[5], sigma[5];
+  double  sum_nn_dist;
+} me_dir_result;
+
+typedef struct {
+  me_dir_result est_to_gt, gt_to_est;
+  double cd[5], f1[5], iou[5];   /* map_eval.cpp:1245-1253 */
+  double full_cd;                /* map_eval.cpp:1429      */
+} me_nn_result;
+
+/* ---- a5-a9: mean map entropy -------------------------------------------------------------------- */
+
+typedef struct {
+  int64_t n_query, n_valid;
+  double  sum_entropy;
+  double  min_entropy, max_entropy;  /* over entropies != 0 (map_eval.cpp:697-701); +inf / -inf if none */
+} me_mme_accum;
+
+typedef struct {
+  double  mme;                       /* sum/n_valid, 0 if none (map_eval.cpp:1720-1724) */
+  int64_t n_valid, n_total;
+  double  min_abs_entropy, max_abs_entropy;  /* |max|, |min| (map_eval.cpp:700-701); NaN if no non-zero entropy */
+} me_mme_result;
+
+/* ---- a10-a16: voxel Gaussians, AWD ("VMD"), SCS ------------------------------------------------ */
+
+typedef struct {
+  double  awd, scs;                  /* vmd (map_eval.cpp:324-325), scs_overall (:387); NaN when the reference divides 0/0 */
+  int64_t n_pairs, n_scs;            /* |wasserstein_distances|, scs_count */
+  int64_t n_voxels_est, n_voxels_gt; /* voxel_map_.size() after buildVoxelMap (voxel_calculator.cpp:55) */
+  int64_t n_active, n_old, n_new;    /* voxel_calculator.cpp:170 */
+} me_awd_result;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+
+int  me_abi_version(void);
+int  me_create(const me_options *opt, me_ctx **out);
+void me_destroy(me_ctx *ctx);
+const char *me_last_error(const me_ctx *ctx);      /* ctx may be NULL: last error of me_create on this thread */
+int  me_set_stream(me_ctx *ctx, void *cuda_stream);
+int  me_set_shard(me_ctx *ctx, int32_t rank, int32_t world);
+int  me_synchronize(me_ctx *ctx);
+
+/* replaces: io::ReadPointCloud* results held in map_3d_/gt_3d_ (map_eval.cpp:10-21) — the clouds the path reads.
+ * me_set_cloud copies host memory (async on the stream; pinned memory makes it truly async);
+ * me_set_cloud_device borrows an fp64 N x 3 device buffer that must outlive the context's use of it. */
+int  me_set_cloud(me_ctx *ctx, int which, const double *xyz_host, int64_t n);
+int  me_set_cloud_device(me_ctx *ctx, int which, const double *xyz_device, int64_t n);
+/* replaces: map_3d_->Transform(initial_matrix) (map_eval.cpp:1206); T is a row-major 4x4 */
+int  me_transform(me_ctx *ctx, int which, const double T[16]);
+/* builds (or rebuilds) the cell-sorted grid of one cloud; the eval calls build lazily if needed */
+int  me_build_grid(me_ctx *ctx, int which);
+
+/* replaces: MapEval::calculateMetricsWithInitialMatrix (map_eval.cpp:1204-1260), getDiffRegResultWithCorrespondence
+ * (:1069-1145), the metric half of calculateMetrics (:1147-1202) and computeChamferDistance (:1398-1431). */
+int  me_eval_nn_accum(me_ctx *ctx, const me_nn_params *p, me_nn_accum *est_to_gt, me_nn_accum *gt_to_est);
+int  me_nn_finalize(const me_nn_params *p, const me_nn_accum *est_to_gt, const me_nn_accum *gt_to_est,
+                    int64_t n_est, int64_t n_gt, me_nn_result *out);      /* host only, no device work */
+int  me_eval_nn(me_ctx *ctx, const me_nn_params *p, me_nn_result *out);   /* accum + finalize, world must be 1 */
+/* per-query nearest neighbour of the last me_eval_nn*, original point order of the QUERY cloud;
+ * which_query = ME_CLOUD_EST -> est->gt sweep.  Only this rank's query range is filled (others -1 / NaN). */
+int  me_get_nn(me_ctx *ctx, int which_query, int32_t *nn_index, double *nn_sqdist);
+
+/* replaces: ComputeMeanMapEntropyUsingNormalTBB / ...UsingNormal (min_neighbors 10, map_eval.cpp:1608-1737, 1538-1606),
+ * ComputeMeanMapEntropy (min_neighbors 5, :1438-1535), ComputeEntropy (:1433-1436) and the min/max side effect of
+ * ColorPointCloudByMME (:697-701).  entropies_host (nullable) receives N fp64, zeros where invalid. */
+int  me_eval_mme_accum(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_accum *out);
+int  me_mme_finalize(const me_mme_accum *acc, int64_t n_total, me_mme_result *out);   /* host only */
+int  me_eval_mme(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_result *out,
+                 double *entropies_host);
+int  me_get_entropies(me_ctx *ctx, int which, double *entropies_host);
+
+/* replaces: MapEval::calculateVMD (map_eval.cpp:240-390) with VoxelCalculator::buildVoxelMap / computeVoxelEntropy /
+ * updateVoxelMap / computeWassersteinDistanceGaussian / getNeighborIndices (voxel_calculator.cpp:7-56,97-172,241-245).
+ * rows27 (nullable): library-allocated n_rows x 27 table = the columns of voxel_errors.txt (map_eval.cpp:292-302),
+ * release with me_free.  Not sharded: every rank computes the whole (cheap) voxel stage. */
+int  me_eval_awd(me_ctx *ctx, double voxel_size, int32_t min_points, int32_t scs_radius, me_awd_result *out,
+                 int64_t *n_rows, double **rows27);
+void me_free(void *p);
+
+/* timing of the last call of each stage in milliseconds (CUDA events on the context's stream):
+ * [0] grid est [1] grid gt [2] nn est->gt [3] nn gt->est [4] mme est [5] mme gt [6] voxel moments [7] awd [8] scs */
+#define ME_N_STAGE_TIMES 9
+int  me_get_stage_times(me_ctx *ctx, double ms[ME_N_STAGE_TIMES]);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t me_launch_count(const me_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPEVAL_B200_H_ */

@@ -1,0 +1,680 @@
+/*
+ * mapeval_oracle.cpp — CPU restatement of MapEval's metric hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ * It is NOT part of the product: libmapeval_b200.so never links, loads or calls it.
+ *
+ * Each function restates one reference function (paths relative to /root/reference/map_eval/src/).
+ * Third-party arithmetic the reference delegates to libraries that are NOT vendored under /root/reference
+ * (Open3D 0.15-0.17 -> nanoflann KD-tree, Eigen 3.3.7) is restated from their published algorithms and
+ * marked [ext]:
+ *   [ext-kd]   nanoflann L2_Adaptor::evalMetric accumulates ((dx*dx)+dy*dy)+dz*dz in double; KNN=1 returns the
+ *              exact nearest neighbour; RadiusResultSet keeps dist < r*r (strict), sorted ascending.
+ *   [ext-norm] Eigen fixed-size Vector3d squaredNorm() is fully unrolled as x*x + (y*y + z*z)
+ *              (redux_novec_unroller splits 3 = 1 + 2); norm() = sqrt(squaredNorm()).
+ *   [ext-det]  Eigen 3x3 determinant = cofactor expansion bruteforce_det3_helper.
+ *   [ext-eig]  SelfAdjointEigenSolver<Matrix3d>::compute = tridiagonal QL; restated as cyclic Jacobi
+ *              (same eigen-pairs to ~1e-15; only the clamped reconstruction V max(L,1e-6) V^T is consumed).
+ *   [ext-llt]  Eigen LLT unblocked in-place lower Cholesky, returning early at the first pivot <= 0.
+ * The reference is built without -march/-ffast-math (CMakeLists.txt:1-49) => no FMA contraction on x86-64;
+ * this file is compiled with -ffp-contract=off to match.
+ *
+ * Parity pinning: the reference ships no tests; the pins are tests/golden/ (the reference's sample output
+ * map_eval/scripts/voxel_errors.txt + voxel_wasserstein_cdf.txt and the README run log AWD 0.35303 / SCS 0.78121),
+ * see tests/test_oracle_golden.py.  The KD-tree boundary itself is unpinned (no fixture exists) and is
+ * cross-checked against scipy.spatial.cKDTree and brute force instead.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/mapeval_b200.h"
+
+namespace {
+
+struct V3 { double x, y, z; };
+
+// ---------------------------------------------------------------------------------------------------
+// exact KD-tree over fp64 points (stands in for open3d::geometry::KDTreeFlann -> nanoflann) [ext-kd]
+// ---------------------------------------------------------------------------------------------------
+struct KdTree {
+  struct Node { int32_t left, right; int32_t begin, end; int32_t dim; double split_lo, split_hi; };
+  const double *pts = nullptr;
+  int64_t n = 0;
+  std::vector<int32_t> idx;
+  std::vector<Node> nodes;
+  static constexpr int kLeaf = 12;
+
+  static inline double d2_kd(const double *a, const double *b) {  // [ext-kd] sequential accumulation
+    double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    double r = dx * dx;
+    r += dy * dy;
+    r += dz * dz;
+    return r;
+  }
+
+  void build(const double *p, int64_t count) {
+    pts = p; n = count;
+    idx.resize(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    nodes.clear();
+    nodes.reserve(2 * (n / kLeaf + 2));
+    if (n > 0) build_rec(0, (int32_t)n);
+  }
+  int32_t build_rec(int32_t b, int32_t e) {
+    int32_t id = (int32_t)nodes.size();
+    nodes.push_back(Node{-1, -1, b, e, -1, 0, 0});
+    if (e - b <= kLeaf) return id;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int32_t i = b; i < e; ++i)
+      for (int d = 0; d < 3; ++d) {
+        double v = pts[3 * (int64_t)idx[i] + d];
+        lo[d] = std::min(lo[d], v); hi[d] = std::max(hi[d], v);
+      }
+    int dim = 0;
+    if (hi[1] - lo[1] > hi[dim] - lo[dim]) dim = 1;
+    if (hi[2] - lo[2] > hi[dim] - lo[dim]) dim = 2;
+    if (hi[dim] == lo[dim]) return id;  // all identical: keep as (large) leaf
+    int32_t m = b + (e - b) / 2;
+    std::nth_element(idx.begin() + b, idx.begin() + m, idx.begin() + e, [&](int32_t a, int32_t c) {
+      double va = pts[3 * (int64_t)a + dim], vc = pts[3 * (int64_t)c + dim];
+      return va < vc || (va == vc && a < c);
+    });
+    double left_max = -1e300, right_min = 1e300;
+    for (int32_t i = b; i < m; ++i) left_max = std::max(left_max, pts[3 * (int64_t)idx[i] + dim]);
+    for (int32_t i = m; i < e; ++i) right_min = std::min(right_min, pts[3 * (int64_t)idx[i] + dim]);
+    int32_t l = build_rec(b, m);
+    int32_t r = build_rec(m, e);
+    nodes[id].left = l; nodes[id].right = r; nodes[id].dim = dim;
+    nodes[id].split_lo = left_max; nodes[id].split_hi = right_min;
+    return id;
+  }
+
+  // exact 1-NN; ties resolved towards the smaller original index
+  void knn1(const double *q, int32_t &best_i, double &best_d2) const {
+    best_i = -1; best_d2 = std::numeric_limits<double>::infinity();
+    if (n == 0) return;
+    knn1_rec(0, q, best_i, best_d2);
+  }
+  void knn1_rec(int32_t id, const double *q, int32_t &bi, double &bd) const {
+    const Node &nd = nodes[id];
+    if (nd.left < 0) {
+      for (int32_t i = nd.begin; i < nd.end; ++i) {
+        int32_t j = idx[i];
+        double d = d2_kd(q, pts + 3 * (int64_t)j);
+        if (d < bd || (d == bd && j < bi)) { bd = d; bi = j; }
+      }
+      return;
+    }
+    double v = q[nd.dim];
+    // distance to each child's slab along dim (0 if inside); computed like a coordinate difference so it never
+    // exceeds the evalMetric value of any point in that child (monotone rounding)
+    double dl = v > nd.split_lo ? v - nd.split_lo : 0.0;
+    double dr = v < nd.split_hi ? nd.split_hi - v : 0.0;
+    int32_t first = nd.left, second = nd.right; double dsecond = dr;
+    if (dr < dl) { first = nd.right; second = nd.left; dsecond = dl; }
+    knn1_rec(first, q, bi, bd);
+    if (dsecond * dsecond <= bd) knn1_rec(second, q, bi, bd);
+  }
+
+  // all points with d2 < r2 (strict) [ext-kd]
+  void radius(const double *q, double r2, std::vector<std::pair<double, int32_t>> &out) const {
+    out.clear();
+    if (n == 0) return;
+    radius_rec(0, q, r2, out);
+  }
+  void radius_rec(int32_t id, const double *q, double r2, std::vector<std::pair<double, int32_t>> &out) const {
+    const Node &nd = nodes[id];
+    if (nd.left < 0) {
+      for (int32_t i = nd.begin; i < nd.end; ++i) {
+        int32_t j = idx[i];
+        double d = d2_kd(q, pts + 3 * (int64_t)j);
+        if (d < r2) out.emplace_back(d, j);
+      }
+      return;
+    }
+    double v = q[nd.dim];
+    double dl = v > nd.split_lo ? v - nd.split_lo : 0.0;
+    double dr = v < nd.split_hi ? nd.split_hi - v : 0.0;
+    if (dl * dl < r2) radius_rec(nd.left, q, r2, out);
+    if (dr * dr < r2) radius_rec(nd.right, q, r2, out);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// small fixed-size algebra, restating the Eigen calls of the path
+// ---------------------------------------------------------------------------------------------------
+inline double sqnorm3(double x, double y, double z) { return x * x + (y * y + z * z); }  // [ext-norm]
+
+inline double det3(const double m[9]) {  // [ext-det]; m row-major
+  auto helper = [&](int a, int b, int c) {
+    return m[0 * 3 + a] * (m[1 * 3 + b] * m[2 * 3 + c] - m[1 * 3 + c] * m[2 * 3 + b]);
+  };
+  return helper(0, 1, 2) - helper(1, 0, 2) + helper(2, 0, 1);
+}
+
+// map_eval.cpp:1433-1436 / :1655-1657
+inline double compute_entropy(const double cov[9]) {
+  return 0.5 * std::log(2 * M_PI * M_E * det3(cov));
+}
+
+// symmetric 3x3 eigen-decomposition, cyclic Jacobi [ext-eig]; a is row-major symmetric; v columns = eigenvectors
+void eig3_jacobi(const double a_in[9], double w[3], double v[9]) {
+  double a[9];
+  std::memcpy(a, a_in, sizeof(a));
+  for (int i = 0; i < 9; ++i) v[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    double diag = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (off <= 1e-34 * diag || off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double apq = a[p * 3 + q];
+        if (apq == 0.0) continue;
+        double app = a[p * 3 + p], aqq = a[q * 3 + q];
+        double theta = (aqq - app) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {  // A <- A * J
+          double akp = a[k * 3 + p], akq = a[k * 3 + q];
+          a[k * 3 + p] = c * akp - s * akq;
+          a[k * 3 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {  // A <- J^T * A
+          double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+          a[p * 3 + k] = c * apk - s * aqk;
+          a[q * 3 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+          v[k * 3 + p] = c * vkp - s * vkq;
+          v[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w[0] = a[0]; w[1] = a[4]; w[2] = a[8];
+}
+
+// in-place lower Cholesky [ext-llt]; returns -1 on success or the failing column (rest left untouched, as Eigen does)
+int llt3_inplace(double m[9]) {
+  for (int k = 0; k < 3; ++k) {
+    double x = m[k * 3 + k];
+    for (int j = 0; j < k; ++j) x -= m[k * 3 + j] * m[k * 3 + j];
+    if (x <= 0.0) return k;
+    x = std::sqrt(x);
+    m[k * 3 + k] = x;
+    for (int i = k + 1; i < 3; ++i) {
+      double s = m[i * 3 + k];
+      for (int j = 0; j < k; ++j) s -= m[i * 3 + j] * m[k * 3 + j];
+      m[i * 3 + k] = s / x;
+    }
+  }
+  return -1;
+}
+inline void lower_of(const double m[9], double l[9]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) l[i * 3 + j] = (j <= i) ? m[i * 3 + j] : 0.0;
+}
+inline void matmul3(const double a[9], const double b[9], double c[9]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += a[i * 3 + k] * b[k * 3 + j];
+      c[i * 3 + j] = s;
+    }
+}
+
+// voxel_calculator.hpp:25-38
+struct VoxelInfo {
+  double mu[3] = {0, 0, 0};
+  double sigma[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int num_points = 0;
+  double entropy = 0, energy = 0;
+  int active = 0;
+  double entropy_old = 0;
+};
+struct Key3 {
+  int32_t k[3];
+  bool operator==(const Key3 &o) const { return k[0] == o.k[0] && k[1] == o.k[1] && k[2] == o.k[2]; }
+};
+// voxel_calculator.hpp:18-22 and map_eval.h:53-58 (same function)
+struct VoxelHasher {
+  std::size_t operator()(const Key3 &key) const {
+    return std::hash<int>()(key.k[0]) ^ std::hash<int>()(key.k[1]) ^ std::hash<int>()(key.k[2]);
+  }
+};
+using VoxelMap = std::unordered_map<Key3, VoxelInfo, VoxelHasher>;
+
+// voxel_calculator.cpp:97-113
+void compute_voxel_entropy(VoxelInfo &voxel) {
+  if (voxel.num_points < 2) {
+    voxel.entropy = 0; voxel.energy = 0;
+  } else {
+    for (double &s : voxel.sigma) s /= (voxel.num_points - 1);
+    double det = det3(voxel.sigma);
+    if (det <= 0) {
+      voxel.entropy = 0; voxel.energy = 0;
+    } else {
+      constexpr double PI = 3.141592653589793238463;
+      voxel.entropy = 0.5 * std::log(std::pow(2 * PI * std::exp(1), 3) * det);
+      voxel.energy = voxel.sigma[0] + voxel.sigma[4] + voxel.sigma[8];
+    }
+  }
+}
+
+// voxel_calculator.cpp:241-245
+inline Key3 voxel_index(const double *p, double vs) {
+  return Key3{{(int32_t)std::floor(p[0] / vs), (int32_t)std::floor(p[1] / vs), (int32_t)std::floor(p[2] / vs)}};
+}
+
+// voxel_calculator.cpp:21-56
+void build_voxel_map(const double *pts, int64_t n, double vs, VoxelMap &map, double *total_entropy) {
+  map.clear();
+  double tot_e = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double *p = pts + 3 * i;
+    Key3 key = voxel_index(p, vs);
+    auto it = map.find(key);
+    if (it == map.end()) {
+      VoxelInfo vi;
+      vi.num_points = 1;
+      vi.mu[0] = p[0]; vi.mu[1] = p[1]; vi.mu[2] = p[2];
+      vi.active = 1;
+      map.emplace(key, vi);
+    } else {
+      VoxelInfo &vi = it->second;
+      vi.num_points++;
+      double delta[3] = {p[0] - vi.mu[0], p[1] - vi.mu[1], p[2] - vi.mu[2]};
+      for (int d = 0; d < 3; ++d) vi.mu[d] += delta[d] / vi.num_points;
+      double after[3] = {p[0] - vi.mu[0], p[1] - vi.mu[1], p[2] - vi.mu[2]};
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) vi.sigma[r * 3 + c] += delta[r] * after[c];
+      vi.energy = vi.sigma[0] + vi.sigma[4] + vi.sigma[8];
+    }
+  }
+  for (auto &kv : map) {
+    VoxelInfo &vi = kv.second;
+    if (vi.num_points > 10) {
+      for (double &s : vi.sigma) s /= (vi.num_points - 1);
+      compute_voxel_entropy(vi);
+      vi.entropy_old = vi.entropy;
+      tot_e += vi.entropy;
+    }
+  }
+  if (total_entropy) *total_entropy = tot_e;
+}
+
+// voxel_calculator.cpp:115-140
+void clamp_cov(const double sigma_stored[9], int num_points, double out[9]) {
+  for (int i = 0; i < 9; ++i) out[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (num_points > 1) {
+    double s[9], sym[9];
+    for (int i = 0; i < 9; ++i) s[i] = sigma_stored[i] / (num_points - 1);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) sym[r * 3 + c] = (s[r * 3 + c] + s[c * 3 + r]) / 2;
+    double w[3], v[9];
+    eig3_jacobi(sym, w, v);
+    for (int k = 0; k < 3; ++k) w[k] = std::max(w[k], 1e-6);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double acc = 0;
+        for (int k = 0; k < 3; ++k) acc += v[r * 3 + k] * w[k] * v[c * 3 + k];
+        out[r * 3 + c] = acc;
+      }
+  }
+}
+double wasserstein_gaussian(const VoxelInfo &v1, const VoxelInfo &v2) {
+  double s1[9], s2[9];
+  clamp_cov(v1.sigma, v1.num_points, s1);
+  clamp_cov(v2.sigma, v2.num_points, s2);
+  double mu_diff[3] = {v1.mu[0] - v2.mu[0], v1.mu[1] - v2.mu[1], v1.mu[2] - v2.mu[2]};
+  double tr_sum = (s1[0] + s2[0]) + (s1[4] + s2[4]) + (s1[8] + s2[8]);
+  double l1m[9], l1[9], l1t[9], tmp[9], a[9];
+  std::memcpy(l1m, s1, sizeof(l1m));
+  llt3_inplace(l1m);
+  lower_of(l1m, l1);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) l1t[r * 3 + c] = l1[c * 3 + r];
+  matmul3(l1, s2, tmp);
+  matmul3(tmp, l1t, a);
+  llt3_inplace(a);
+  double tr_sqrt = a[0] + a[4] + a[8];
+  double distance = (mu_diff[0] * mu_diff[0] + mu_diff[1] * mu_diff[1] + mu_diff[2] * mu_diff[2]) + tr_sum - 2 * tr_sqrt;
+  return std::sqrt(std::max(0.0, distance));
+}
+
+// map_eval.cpp:351-387 over an explicit (key -> W) table
+void scs_from_table(const std::unordered_map<Key3, double, VoxelHasher> &wd, int radius, double *scs, int64_t *count) {
+  double total_scs = 0.0;
+  int64_t scs_count = 0;
+  std::vector<double> nb;
+  for (const auto &kv : wd) {
+    const Key3 &index = kv.first;
+    nb.clear();
+    for (int dx = -radius; dx <= radius; ++dx)           // voxel_calculator.cpp:7-19
+      for (int dy = -radius; dy <= radius; ++dy)
+        for (int dz = -radius; dz <= radius; ++dz) {
+          if (dx == 0 && dy == 0 && dz == 0) continue;
+          Key3 k{{index.k[0] + dx, index.k[1] + dy, index.k[2] + dz}};
+          auto it = wd.find(k);
+          if (it != wd.end()) nb.push_back(it->second);
+        }
+    if (!nb.empty()) {
+      double mean = std::accumulate(nb.begin(), nb.end(), 0.0) / nb.size();
+      double var = 0.0;
+      for (double w : nb) var += (w - mean) * (w - mean);
+      var /= nb.size();
+      total_scs += std::sqrt(var) / mean;
+      scs_count++;
+    }
+  }
+  *scs = total_scs / scs_count;  // 0/0 -> NaN exactly as map_eval.cpp:387
+  *count = scs_count;
+}
+
+// map_eval.cpp:1069-1145 (== :990-1067; :828-897 differs only in integer counters)
+void diff_reg_result(const std::vector<std::pair<int32_t, int32_t>> &pairs, const double *source, int64_t n_source,
+                     const double *target, int64_t n_target, const double tau[5], me_dir_result *out) {
+  std::memset(out, 0, sizeof(*out));
+  std::vector<double> dis;
+  dis.reserve(pairs.size());
+  double number_vec[5] = {0}, mean_vec[5] = {0}, rmse_vec[5] = {0};
+  int64_t n_ub = 0;
+  for (const auto &pr : pairs) {
+    // the reference indexes with operator[] and no bounds check; out-of-range = UB there, dropped + counted here
+    if (pr.first < 0 || pr.first >= n_source || pr.second < 0 || pr.second >= n_target) { ++n_ub; continue; }
+    const double *a = source + 3 * (int64_t)pr.first, *b = target + 3 * (int64_t)pr.second;
+    double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    double sq = sqnorm3(dx, dy, dz);
+    double nd = std::sqrt(sq);
+    dis.push_back(nd);
+    for (int k = 0; k < 5; ++k)
+      if (nd <= tau[k]) { mean_vec[k] += nd; rmse_vec[k] += sq; number_vec[k]++; }
+  }
+  const double nc = (double)dis.size();
+  out->n_source = n_source;
+  out->n_corr = (int64_t)dis.size();
+  out->n_ub = n_ub;
+  int target_num = (int)n_source;
+  for (int k = 0; k < 5; ++k) {
+    mean_vec[k] /= nc;
+    rmse_vec[k] /= nc;
+  }
+  for (int k = 0; k < 5; ++k) {
+    out->fitness[k] = number_vec[k] * 1.0 / target_num;
+    out->rmse[k] = std::sqrt(rmse_vec[k]);
+    double sigma = 0.0;
+    for (double d : dis) { double e = d - mean_vec[k]; sigma += std::pow(e, 2); }
+    sigma /= nc;
+    out->sigma[k] = std::sqrt(sigma);
+    out->mean[k] = mean_vec[k];
+    out->n_inlier[k] = (int64_t)number_vec[k];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// open3d PointCloud::Transform [ext]: p' = (T * [p,1]).head<3>() / w, evaluated per row as a 4-term dot product
+void oracle_transform(double *xyz, int64_t n, const double T[16]) {
+  for (int64_t i = 0; i < n; ++i) {
+    double *p = xyz + 3 * i;
+    double x = p[0], y = p[1], z = p[2], o[4];
+    for (int r = 0; r < 4; ++r) o[r] = T[r * 4 + 0] * x + T[r * 4 + 1] * y + T[r * 4 + 2] * z + T[r * 4 + 3] * 1.0;
+    p[0] = o[0] / o[3]; p[1] = o[1] / o[3]; p[2] = o[2] / o[3];
+  }
+}
+
+// exact 1-NN of every query in `ref`: index + squared distance [ext-kd]
+int oracle_knn1(const double *query, int64_t nq, const double *ref, int64_t nr, int32_t *nn_idx, double *nn_d2,
+                int threads) {
+  KdTree tree;
+  tree.build(ref, nr);
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t i = 0; i < nq; ++i) {
+    int32_t bi; double bd;
+    tree.knn1(query + 3 * i, bi, bd);
+    nn_idx[i] = bi; nn_d2[i] = bd;
+  }
+  return 0;
+}
+
+// map_eval.cpp:1204-1260 (+ :1398-1431 when want_full_cd).  `threads`: 1 = as serial as the reference's path A,
+// >1 = all-cores mode (results identical except fp summation order of sum_nn_dist).
+int oracle_eval_nn(const double *est, int64_t n_est, const double *gt, int64_t n_gt, const me_nn_params *p,
+                   me_nn_result *out, int32_t *nn_est_to_gt, int32_t *nn_gt_to_est, int threads) {
+  std::memset(out, 0, sizeof(*out));
+  if (n_est <= 0 || n_gt <= 0) return ME_ERR_EMPTY;
+  const int dirs = p->directions ? p->directions : 3;
+  auto keep = [&](double d2) {
+    return p->cutoff_mode == ME_CUTOFF_SQDIST_LE_R ? (d2 <= p->icp_max_distance)
+                                                   : (d2 < p->icp_max_distance * p->icp_max_distance);
+  };
+  std::vector<int32_t> idx;
+  std::vector<double> d2;
+  double sum_p_to_q = 0.0, sum_q_to_p = 0.0;
+  if (dirs & 1) {
+    idx.resize(n_est); d2.resize(n_est);
+    oracle_knn1(est, n_est, gt, n_gt, idx.data(), d2.data(), threads);
+    std::vector<std::pair<int32_t, int32_t>> corr;   // (i_est, nn_gt)  map_eval.cpp:1220
+    for (int64_t i = 0; i < n_est; ++i) {
+      if (keep(d2[i])) corr.emplace_back((int32_t)i, idx[i]);
+      sum_p_to_q += std::sqrt(d2[i]);                 // map_eval.cpp:1416
+    }
+    if (nn_est_to_gt) std::memcpy(nn_est_to_gt, idx.data(), sizeof(int32_t) * n_est);
+    diff_reg_result(corr, est, n_est, gt, n_gt, p->tau, &out->est_to_gt);   // map_eval.cpp:1239
+    out->est_to_gt.sum_nn_dist = sum_p_to_q;
+  }
+  if (dirs & 2) {
+    idx.resize(n_gt); d2.resize(n_gt);
+    oracle_knn1(gt, n_gt, est, n_est, idx.data(), d2.data(), threads);
+    std::vector<std::pair<int32_t, int32_t>> corr;
+    for (int64_t i = 0; i < n_gt; ++i) {
+      if (keep(d2[i])) {
+        if (p->pairing == ME_PAIRING_AS_WRITTEN) corr.emplace_back(idx[i], (int32_t)i);  // (nn_est, i_gt) map_eval.cpp:1233
+        else corr.emplace_back((int32_t)i, idx[i]);
+      }
+      sum_q_to_p += std::sqrt(d2[i]);                 // map_eval.cpp:1425
+    }
+    if (nn_gt_to_est) std::memcpy(nn_gt_to_est, idx.data(), sizeof(int32_t) * n_gt);
+    // map_eval.cpp:1241: source = gt, target = est — with the pair order above this reads gt[nn_est], est[i_gt]
+    diff_reg_result(corr, gt, n_gt, est, n_est, p->tau, &out->gt_to_est);
+    out->gt_to_est.sum_nn_dist = sum_q_to_p;
+  }
+  for (int k = 0; k < 5; ++k) {                        // map_eval.cpp:1245-1253
+    out->cd[k] = out->est_to_gt.rmse[k] + out->gt_to_est.rmse[k];
+    double overlap = out->est_to_gt.fitness[k], rmse = out->est_to_gt.rmse[k];
+    out->f1[k] = 2 * overlap * rmse / (overlap + rmse);
+    int num_intersection = (int)out->est_to_gt.n_inlier[k];
+    int num_union = (int)(n_est + n_gt - num_intersection);
+    out->iou[k] = (double)num_intersection / num_union;
+  }
+  out->full_cd = p->want_full_cd ? (sum_p_to_q / (double)n_est + sum_q_to_p / (double)n_gt) : 0.0;  // :1429
+  return 0;
+}
+
+// map_eval.cpp:1608-1737 (min_neighbors = 10), :1538-1606 (10), :1438-1535 (5); + :697-701 extrema
+int oracle_eval_mme(const double *xyz, int64_t n, double radius, int32_t min_neighbors, me_mme_result *out,
+                    double *entropies, int threads) {
+  std::memset(out, 0, sizeof(*out));
+  if (n <= 0) return ME_ERR_EMPTY;
+  KdTree tree;
+  tree.build(xyz, n);
+  const double r2 = radius * radius;   // open3d SearchRadius passes radius*radius to nanoflann [ext-kd]
+  std::vector<double> ent_local;
+  double *ent = entropies;
+  if (!ent) { ent_local.assign(n, 0.0); ent = ent_local.data(); }
+  else std::fill(ent, ent + n, 0.0);
+  double sum_entropy = 0.0;
+  int64_t valid = 0;
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel reduction(+ : sum_entropy, valid)
+  {
+    std::vector<std::pair<double, int32_t>> res;
+    std::vector<double> cen;
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; ++i) {
+      tree.radius(xyz + 3 * i, r2, res);
+      if (res.empty()) continue;                      // SearchRadius(...) > 0
+      std::sort(res.begin(), res.end());              // nanoflann sorted=true
+      const size_t k = res.size() - 1;                // erase(begin()) — the query itself
+      if ((int64_t)k < (int64_t)min_neighbors) continue;
+      double mean[3] = {0, 0, 0};
+      for (size_t j = 1; j <= k; ++j) {
+        const double *q = xyz + 3 * (int64_t)res[j].second;
+        mean[0] += q[0]; mean[1] += q[1]; mean[2] += q[2];
+      }
+      mean[0] /= (double)k; mean[1] /= (double)k; mean[2] /= (double)k;
+      double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (size_t j = 1; j <= k; ++j) {
+        const double *q = xyz + 3 * (int64_t)res[j].second;
+        double c[3] = {q[0] - mean[0], q[1] - mean[1], q[2] - mean[2]};
+        for (int r = 0; r < 3; ++r)
+          for (int cc = 0; cc < 3; ++cc) cov[r * 3 + cc] += c[r] * c[cc];
+      }
+      for (double &v : cov) v /= (double)(k - 1);
+      double e = compute_entropy(cov);
+      if (!std::isnan(e) && !std::isinf(e)) {
+        sum_entropy += e;
+        ent[i] = e;
+        ++valid;
+      }
+    }
+  }
+  out->n_total = n;
+  out->n_valid = valid;
+  out->mme = valid > 0 ? sum_entropy / (double)valid : 0.0;
+  // ColorPointCloudByMME, map_eval.cpp:697-701 (dereferencing end() when empty is UB there; NaN here)
+  double mn = std::numeric_limits<double>::infinity(), mx = -mn;
+  for (int64_t i = 0; i < n; ++i)
+    if (ent[i] != 0.0) { mn = std::min(mn, ent[i]); mx = std::max(mx, ent[i]); }
+  if (mn <= mx) { out->max_abs_entropy = std::fabs(mn); out->min_abs_entropy = std::fabs(mx); }
+  else { out->max_abs_entropy = out->min_abs_entropy = std::numeric_limits<double>::quiet_NaN(); }
+  return 0;
+}
+
+// map_eval.cpp:240-390
+int oracle_eval_awd(const double *est, int64_t n_est, const double *gt, int64_t n_gt, double voxel_size,
+                    int32_t min_points, int32_t scs_radius, me_awd_result *out, int64_t *n_rows, double **rows27) {
+  std::memset(out, 0, sizeof(*out));
+  VoxelMap gt_map, est_map;
+  build_voxel_map(gt, n_gt, voxel_size, gt_map, nullptr);      // :248
+  build_voxel_map(est, n_est, voxel_size, est_map, nullptr);   // :249
+  out->n_voxels_gt = (int64_t)gt_map.size();
+  out->n_voxels_est = (int64_t)est_map.size();
+  // voxel_calculator.cpp:142-172
+  int64_t old_n = 0, active_n = 0, new_n = 0;
+  for (auto &kv : est_map) kv.second.active = 2;
+  for (const auto &gkv : gt_map) {
+    auto it = est_map.find(gkv.first);
+    if (it != est_map.end()) { it->second.active = 1; active_n++; }
+    else { VoxelInfo vi; vi.active = 0; est_map[gkv.first] = vi; old_n++; }
+  }
+  for (const auto &kv : est_map) if (kv.second.active == 2) new_n++;
+  out->n_active = active_n; out->n_old = old_n; out->n_new = new_n;
+
+  std::unordered_map<Key3, double, VoxelHasher> wd;
+  std::vector<double> rows;
+  for (const auto &kv : est_map) {                             // :269-305
+    const VoxelInfo &ev = kv.second;
+    if (ev.active != 1) continue;
+    auto git = gt_map.find(kv.first);
+    if (git == gt_map.end()) continue;
+    const VoxelInfo &gv = git->second;
+    if (ev.num_points < min_points || gv.num_points < min_points) continue;
+    double ws = wasserstein_gaussian(gv, ev);                  // (gt_voxel, est_voxel) :284
+    wd[kv.first] = ws;
+    if (rows27) {
+      double row[27];
+      for (int d = 0; d < 3; ++d) {
+        row[d] = (double)kv.first.k[d] * voxel_size;
+        row[3 + d] = ((double)kv.first.k[d] + 1.0) * voxel_size;
+        row[6 + d] = ev.mu[d];
+        row[18 + d] = gv.mu[d];
+      }
+      row[9] = ws; row[10] = gv.num_points; row[11] = ev.num_points;
+      const int tri[6] = {0, 1, 2, 4, 5, 8};
+      for (int t = 0; t < 6; ++t) { row[12 + t] = ev.sigma[tri[t]]; row[21 + t] = gv.sigma[tri[t]]; }
+      rows.insert(rows.end(), row, row + 27);
+    }
+  }
+  std::vector<double> ws_distances;                             // :314-325
+  for (const auto &kv : wd) ws_distances.push_back(kv.second);
+  out->n_pairs = (int64_t)ws_distances.size();
+  out->awd = std::accumulate(ws_distances.begin(), ws_distances.end(), 0.0) / ws_distances.size();
+  scs_from_table(wd, scs_radius, &out->scs, &out->n_scs);      // :351-387
+  if (n_rows) *n_rows = out->n_pairs;
+  if (rows27) {
+    *rows27 = (double *)std::malloc(std::max<size_t>(1, rows.size()) * sizeof(double));
+    if (!*rows27) return ME_ERR_NOMEM;
+    std::memcpy(*rows27, rows.data(), rows.size() * sizeof(double));
+  }
+  return 0;
+}
+
+void oracle_free(void *p) { std::free(p); }
+
+// voxel_calculator.cpp:115-140 on raw stored values — used by the golden-fixture known-answer test
+double oracle_wasserstein(const double mu1[3], const double sigma1[9], int n1, const double mu2[3],
+                          const double sigma2[9], int n2) {
+  VoxelInfo a, b;
+  std::memcpy(a.mu, mu1, sizeof(a.mu)); std::memcpy(a.sigma, sigma1, sizeof(a.sigma)); a.num_points = n1;
+  std::memcpy(b.mu, mu2, sizeof(b.mu)); std::memcpy(b.sigma, sigma2, sizeof(b.sigma)); b.num_points = n2;
+  return wasserstein_gaussian(a, b);
+}
+
+// map_eval.cpp:351-387 on an explicit voxel-index / W table
+int oracle_scs(const int32_t *keys3, const double *w, int64_t n, int radius, double *scs, int64_t *count) {
+  std::unordered_map<Key3, double, VoxelHasher> wd;
+  for (int64_t i = 0; i < n; ++i) wd[Key3{{keys3[3 * i], keys3[3 * i + 1], keys3[3 * i + 2]}}] = w[i];
+  scs_from_table(wd, radius, scs, count);
+  return 0;
+}
+
+// per-voxel Gaussians exactly as stored after buildVoxelMap (voxel_calculator.cpp:21-56): for tests
+int oracle_voxel_map(const double *xyz, int64_t n, double voxel_size, int64_t *n_voxels, int32_t **keys3,
+                     int32_t **counts, double **mu3, double **sigma9) {
+  VoxelMap m;
+  build_voxel_map(xyz, n, voxel_size, m, nullptr);
+  size_t nv = m.size();
+  *n_voxels = (int64_t)nv;
+  *keys3 = (int32_t *)std::malloc(std::max<size_t>(1, nv) * 3 * sizeof(int32_t));
+  *counts = (int32_t *)std::malloc(std::max<size_t>(1, nv) * sizeof(int32_t));
+  *mu3 = (double *)std::malloc(std::max<size_t>(1, nv) * 3 * sizeof(double));
+  *sigma9 = (double *)std::malloc(std::max<size_t>(1, nv) * 9 * sizeof(double));
+  size_t i = 0;
+  for (const auto &kv : m) {
+    std::memcpy(*keys3 + 3 * i, kv.first.k, 3 * sizeof(int32_t));
+    (*counts)[i] = kv.second.num_points;
+    std::memcpy(*mu3 + 3 * i, kv.second.mu, 3 * sizeof(double));
+    std::memcpy(*sigma9 + 9 * i, kv.second.sigma, 9 * sizeof(double));
+    ++i;
+  }
+  return 0;
+}
+
+}  // extern "C"
