@@ -27,7 +27,8 @@ STAGE_NAMES = ("grid_est", "grid_gt", "nn_est_to_gt", "nn_gt_to_est", "mme_est",
 
 class me_options(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("stream", C.c_void_p), ("nn_cell_size", C.c_double), ("max_grid_cells", C.c_int64)]
+                ("stream", C.c_void_p), ("nn_cell_size", C.c_double), ("max_grid_cells", C.c_int64),
+                ("vmd_voxel_size", C.c_double)]
 
 
 class me_nn_params(C.Structure):

@@ -1,0 +1,335 @@
+// api.cu — the C-ABI of libmapeval_b200.so (include/mapeval_b200.h): context lifecycle, cloud upload, host-side
+// finalisation of the sum-reducible accumulators.  No CPU fallback exists: every evaluation runs the sm_100a kernels.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+
+static thread_local std::string g_create_error;
+
+namespace me {
+
+int fail(me_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int ensure(me_ctx *ctx, void **ptr, long long *cap, long long need, size_t elem) {
+  if (*ptr && *cap >= need) return ME_OK;
+  if (*ptr) { cudaFree(*ptr); *ptr = nullptr; *cap = 0; }
+  long long want = std::max<long long>(need, 1);
+  cudaError_t e = cudaMalloc(ptr, (size_t)want * elem);
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    cudaGetLastError();
+    return fail(ctx, ME_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string((size_t)want * elem) + " bytes: " + cudaGetErrorString(e));
+  }
+  *cap = want;
+  return ME_OK;
+}
+
+int ensure_work(me_ctx *ctx, size_t bytes) {
+  if (ctx->d_work && ctx->work_bytes >= bytes) return ME_OK;
+  if (ctx->d_work) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_work); ctx->d_work = nullptr; ctx->work_bytes = 0; }
+  size_t want = std::max<size_t>(bytes, 1 << 20);
+  cudaError_t e = cudaMalloc(&ctx->d_work, want);
+  if (e != cudaSuccess) {
+    ctx->d_work = nullptr;
+    cudaGetLastError();
+    return fail(ctx, ME_ERR_NOMEM, std::string("cudaMalloc(work) of ") + std::to_string(want) + " bytes: " + cudaGetErrorString(e));
+  }
+  ctx->work_bytes = want;
+  return ME_OK;
+}
+
+static void invalidate(Cloud &c) {
+  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false;
+}
+
+static void free_cloud(Cloud &c) {
+  if (c.owned && c.d_xyz) cudaFree(c.d_xyz);
+  if (c.d_sorted) cudaFree(c.d_sorted);
+  if (c.d_cell_off) cudaFree(c.d_cell_off);
+  if (c.d_cell_id) cudaFree(c.d_cell_id);
+  if (c.d_nn_idx) cudaFree(c.d_nn_idx);
+  if (c.d_nn_d2) cudaFree(c.d_nn_d2);
+  if (c.d_entropy) cudaFree(c.d_entropy);
+  c = Cloud();
+}
+
+}  // namespace me
+
+using namespace me;
+
+static constexpr size_t kScratchBytes = 4096;
+
+#define ME_ENTER(ctx)                                                                    \
+  if (!(ctx)) return ME_ERR_INVALID;                                                     \
+  do {                                                                                   \
+    cudaError_t e__ = cudaSetDevice((ctx)->device);                                      \
+    if (e__ != cudaSuccess) return me::fail((ctx), ME_ERR_CUDA, cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" {
+
+int me_abi_version(void) { return ME_ABI_VERSION; }
+
+int me_create(const me_options *opt, me_ctx **out) {
+  if (!out) return ME_ERR_INVALID;
+  *out = nullptr;
+  if (!opt || opt->abi_version != ME_ABI_VERSION) return fail(nullptr, ME_ERR_INVALID, "me_options.abi_version mismatch");
+  if (opt->world < 1 || opt->rank < 0 || opt->rank >= opt->world) return fail(nullptr, ME_ERR_INVALID, "bad rank/world");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, ME_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                               " (libmapeval_b200 has no CPU path)");
+  }
+  if (opt->device < 0 || opt->device >= ndev) return fail(nullptr, ME_ERR_NO_DEVICE, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, opt->device) != cudaSuccess) return fail(nullptr, ME_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, ME_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                               std::to_string(prop.minor) + "; this library carries sm_100a code only");
+  if (cudaSetDevice(opt->device) != cudaSuccess) return fail(nullptr, ME_ERR_CUDA, "cudaSetDevice failed");
+  me_ctx *ctx = new (std::nothrow) me_ctx();
+  if (!ctx) return fail(nullptr, ME_ERR_NOMEM, "out of host memory");
+  ctx->device = opt->device;
+  ctx->rank = opt->rank; ctx->world = opt->world;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->nn_cell_size = opt->nn_cell_size > 0 ? opt->nn_cell_size : 0.0;
+  ctx->max_grid_cells = opt->max_grid_cells > 0 ? std::min<long long>(opt->max_grid_cells, 0xfffffff0ll) : (1ll << 28);
+  ctx->voxel_hint = opt->vmd_voxel_size > 0 ? opt->vmd_voxel_size : 0.0;
+  if (opt->stream) { ctx->stream = (cudaStream_t)opt->stream; ctx->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, ME_ERR_CUDA, "cudaStreamCreate failed"); }
+    ctx->own_stream = true;
+  }
+  bool ok = cudaMalloc(&ctx->d_scratch, kScratchBytes) == cudaSuccess && cudaMallocHost(&ctx->h_pinned, kScratchBytes) == cudaSuccess;
+  for (int i = 0; ok && i < 2 * ME_N_STAGE_TIMES; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  for (int i = 0; i < ME_N_STAGE_TIMES; ++i) ctx->ev_used[i] = false;
+  if (!ok) { me_destroy(ctx); return fail(nullptr, ME_ERR_NOMEM, "context allocation failed"); }
+  ctx->scratch_bytes = kScratchBytes;
+  *out = ctx;
+  return ME_OK;
+}
+
+void me_destroy(me_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_cloud(ctx->cloud[0]);
+  free_cloud(ctx->cloud[1]);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->d_work) cudaFree(ctx->d_work);
+  for (int i = 0; i < 2 * ME_N_STAGE_TIMES; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *me_last_error(const me_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int me_set_stream(me_ctx *ctx, void *cuda_stream) {
+  ME_ENTER(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+  if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
+  else {
+    ME_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return ME_OK;
+}
+
+int me_set_shard(me_ctx *ctx, int32_t rank, int32_t world) {
+  ME_ENTER(ctx);
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, ME_ERR_INVALID, "bad rank/world");
+  ctx->rank = rank; ctx->world = world;
+  ctx->cloud[0].nn_valid = ctx->cloud[1].nn_valid = false;
+  ctx->cloud[0].entropy_valid = ctx->cloud[1].entropy_valid = false;
+  return ME_OK;
+}
+
+int me_synchronize(me_ctx *ctx) {
+  ME_ENTER(ctx);
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ME_OK;
+}
+
+int me_set_cloud(me_ctx *ctx, int which, const double *xyz_host, int64_t n) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "which must be ME_CLOUD_EST or ME_CLOUD_GT");
+  if (n < 0 || (n > 0 && !xyz_host)) return fail(ctx, ME_ERR_INVALID, "bad cloud pointer/size");
+  if (n >= 0x7fffffffll) return fail(ctx, ME_ERR_RANGE, "more than 2^31-1 points per cloud (the reference indexes with int)");
+  Cloud &c = ctx->cloud[which];
+  if (!c.owned) { c.d_xyz = nullptr; c.cap_xyz = 0; }
+  ME_TRY(ensure(ctx, (void **)&c.d_xyz, &c.cap_xyz, 3 * n, sizeof(double)));
+  c.owned = true;
+  c.n = n;
+  invalidate(c);
+  if (n > 0) ME_CUDA(ctx, cudaMemcpyAsync(c.d_xyz, xyz_host, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return ME_OK;
+}
+
+int me_set_cloud_device(me_ctx *ctx, int which, const double *xyz_device, int64_t n) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "which must be ME_CLOUD_EST or ME_CLOUD_GT");
+  if (n < 0 || (n > 0 && !xyz_device)) return fail(ctx, ME_ERR_INVALID, "bad cloud pointer/size");
+  if (n >= 0x7fffffffll) return fail(ctx, ME_ERR_RANGE, "more than 2^31-1 points per cloud");
+  Cloud &c = ctx->cloud[which];
+  if (c.owned && c.d_xyz) { cudaStreamSynchronize(ctx->stream); cudaFree(c.d_xyz); }
+  c.d_xyz = const_cast<double *>(xyz_device);
+  c.cap_xyz = 0;
+  c.owned = false;
+  c.n = n;
+  invalidate(c);
+  return ME_OK;
+}
+
+int me_transform(me_ctx *ctx, int which, const double T[16]) {
+  ME_ENTER(ctx);
+  if ((which != ME_CLOUD_EST && which != ME_CLOUD_GT) || !T) return fail(ctx, ME_ERR_INVALID, "bad arguments");
+  return transform_cloud(ctx, which, T);
+}
+
+int me_build_grid(me_ctx *ctx, int which) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad cloud id");
+  ctx->cloud[which].grid_valid = false;
+  return build_grid(ctx, which);
+}
+
+int me_eval_nn_accum(me_ctx *ctx, const me_nn_params *p, me_nn_accum *est_to_gt, me_nn_accum *gt_to_est) {
+  ME_ENTER(ctx);
+  if (!p) return fail(ctx, ME_ERR_INVALID, "null params");
+  if (p->cutoff_mode != ME_CUTOFF_SQDIST_LE_R && p->cutoff_mode != ME_CUTOFF_DIST_LT_R) return fail(ctx, ME_ERR_INVALID, "bad cutoff_mode");
+  if (p->pairing != ME_PAIRING_AS_WRITTEN && p->pairing != ME_PAIRING_GEOMETRIC) return fail(ctx, ME_ERR_INVALID, "bad pairing");
+  const int dirs = p->directions ? p->directions : 3;
+  if (((dirs & 1) && !est_to_gt) || ((dirs & 2) && !gt_to_est)) return fail(ctx, ME_ERR_INVALID, "null accumulator for a requested direction");
+  return run_nn(ctx, p, est_to_gt, gt_to_est);
+}
+
+static void finalize_dir(const me_nn_accum *a, int64_t n_source, me_dir_result *r) {
+  std::memset(r, 0, sizeof(*r));
+  r->n_source = n_source;
+  r->n_corr = a->n_corr;
+  r->n_ub = a->n_ub;
+  r->sum_nn_dist = a->sum_nn_dist;
+  const double nc = (double)a->n_corr;
+  const int target_num = (int)n_source;                       // map_eval.cpp:1128
+  for (int k = 0; k < 5; ++k) {
+    r->n_inlier[k] = a->n_inlier[k];
+    const double mean = a->sum_d[k] / nc;                      // :1125
+    r->mean[k] = mean;
+    r->rmse[k] = std::sqrt(a->sum_d2[k] / nc);                 // :1126,1131
+    r->fitness[k] = (double)a->n_inlier[k] * 1.0 / target_num; // :1130
+    // :1132-1138, sum over ALL kept pairs of (d - mean_k)^2, in closed form
+    double ss = a->sum_d2_all - 2.0 * mean * a->sum_d_all + nc * mean * mean;
+    if (ss < 0 && ss > -1e-9 * a->sum_d2_all) ss = 0;
+    r->sigma[k] = std::sqrt(ss / nc);
+  }
+}
+
+int me_nn_finalize(const me_nn_params *p, const me_nn_accum *est_to_gt, const me_nn_accum *gt_to_est, int64_t n_est,
+                   int64_t n_gt, me_nn_result *out) {
+  if (!p || !out) return ME_ERR_INVALID;
+  std::memset(out, 0, sizeof(*out));
+  me_nn_accum zero;
+  std::memset(&zero, 0, sizeof(zero));
+  const int dirs = p->directions ? p->directions : 3;
+  if (dirs & 1) finalize_dir(est_to_gt ? est_to_gt : &zero, n_est, &out->est_to_gt);
+  if (dirs & 2) finalize_dir(gt_to_est ? gt_to_est : &zero, n_gt, &out->gt_to_est);
+  for (int k = 0; k < 5; ++k) {                                 // map_eval.cpp:1245-1253
+    out->cd[k] = out->est_to_gt.rmse[k] + out->gt_to_est.rmse[k];
+    const double overlap = out->est_to_gt.fitness[k], rmse = out->est_to_gt.rmse[k];
+    out->f1[k] = 2 * overlap * rmse / (overlap + rmse);
+    const int num_intersection = (int)out->est_to_gt.n_inlier[k];
+    const int num_union = (int)(n_est + n_gt - num_intersection);
+    out->iou[k] = (double)num_intersection / num_union;
+  }
+  out->full_cd = p->want_full_cd ? (out->est_to_gt.sum_nn_dist / (double)n_est + out->gt_to_est.sum_nn_dist / (double)n_gt) : 0.0;
+  return ME_OK;
+}
+
+int me_eval_nn(me_ctx *ctx, const me_nn_params *p, me_nn_result *out) {
+  ME_ENTER(ctx);
+  if (!p || !out) return fail(ctx, ME_ERR_INVALID, "null argument");
+  if (ctx->world != 1) return fail(ctx, ME_ERR_INVALID, "me_eval_nn needs world == 1; use me_eval_nn_accum + all-reduce + me_nn_finalize");
+  me_nn_accum a, b;
+  ME_TRY(me_eval_nn_accum(ctx, p, &a, &b));
+  return me_nn_finalize(p, &a, &b, ctx->cloud[0].n, ctx->cloud[1].n, out);
+}
+
+int me_get_nn(me_ctx *ctx, int which_query, int32_t *nn_index, double *nn_sqdist) {
+  ME_ENTER(ctx);
+  if (which_query != ME_CLOUD_EST && which_query != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad cloud id");
+  return unsort_nn(ctx, which_query, nn_index, nn_sqdist);
+}
+
+int me_eval_mme_accum(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_accum *out) {
+  ME_ENTER(ctx);
+  if ((which != ME_CLOUD_EST && which != ME_CLOUD_GT) || !out) return fail(ctx, ME_ERR_INVALID, "bad arguments");
+  return run_mme(ctx, which, radius, min_neighbors, out);
+}
+
+int me_mme_finalize(const me_mme_accum *acc, int64_t n_total, me_mme_result *out) {
+  if (!acc || !out) return ME_ERR_INVALID;
+  out->n_total = n_total;
+  out->n_valid = acc->n_valid;
+  out->mme = acc->n_valid > 0 ? acc->sum_entropy / (double)acc->n_valid : 0.0;   // map_eval.cpp:1720-1724
+  if (acc->min_entropy <= acc->max_entropy) {                                     // :700-701
+    out->max_abs_entropy = std::fabs(acc->min_entropy);
+    out->min_abs_entropy = std::fabs(acc->max_entropy);
+  } else {
+    out->max_abs_entropy = out->min_abs_entropy = std::numeric_limits<double>::quiet_NaN();
+  }
+  return ME_OK;
+}
+
+int me_get_entropies(me_ctx *ctx, int which, double *entropies_host) {
+  ME_ENTER(ctx);
+  if ((which != ME_CLOUD_EST && which != ME_CLOUD_GT) || !entropies_host) return fail(ctx, ME_ERR_INVALID, "bad arguments");
+  return unsort_entropy(ctx, which, entropies_host);
+}
+
+int me_eval_mme(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_result *out, double *entropies_host) {
+  ME_ENTER(ctx);
+  if (!out) return fail(ctx, ME_ERR_INVALID, "null result");
+  if (ctx->world != 1) return fail(ctx, ME_ERR_INVALID, "me_eval_mme needs world == 1; use me_eval_mme_accum + all-reduce + me_mme_finalize");
+  me_mme_accum acc;
+  ME_TRY(me_eval_mme_accum(ctx, which, radius, min_neighbors, &acc));
+  ME_TRY(me_mme_finalize(&acc, ctx->cloud[which].n, out));
+  if (entropies_host) ME_TRY(unsort_entropy(ctx, which, entropies_host));
+  return ME_OK;
+}
+
+int me_eval_awd(me_ctx *ctx, double voxel_size, int32_t min_points, int32_t scs_radius, me_awd_result *out,
+                int64_t *n_rows, double **rows27) {
+  ME_ENTER(ctx);
+  if (!out) return fail(ctx, ME_ERR_INVALID, "null result");
+  return run_awd(ctx, voxel_size, min_points, scs_radius, out, n_rows, rows27);
+}
+
+void me_free(void *p) { std::free(p); }
+
+int me_get_stage_times(me_ctx *ctx, double ms[ME_N_STAGE_TIMES]) {
+  ME_ENTER(ctx);
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < ME_N_STAGE_TIMES; ++s) {
+    ms[s] = 0.0;
+    if (!ctx->ev_used[s]) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->ev[2 * s], ctx->ev[2 * s + 1]) == cudaSuccess) ms[s] = t;
+    else cudaGetLastError();
+  }
+  return ME_OK;
+}
+
+int64_t me_launch_count(const me_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// common.cuh — context, lattice and device helpers shared by the kernels of libmapeval_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include "../../include/mapeval_b200.h"
+
+namespace me {
+
+// One point of a cell-sorted cloud: absolute fp64 coordinates (the reference's storage type,
+// std::vector<Eigen::Vector3d>) + the index the point had in the caller's array.  32 B, so a point is two
+// aligned 16-byte loads.
+struct __align__(32) P4 {
+  double x, y, z;
+  long long idx;
+};
+
+// Dense lattice of a cloud.  Cells are cubes of edge h = v / m whose boundaries coincide with the voxel
+// boundaries floor(x / v) of the reference (voxel_calculator.cpp:241-245): every cell belongs to exactly one
+// voxel, so the voxel stage needs no hashing and no atomics.  Without a voxel size v := h, m := 1.
+struct Lattice {
+  double v;          // voxel edge
+  double h;          // cell edge = v / m
+  double m_over_v;   // m / v
+  int m;             // cells per voxel edge
+  int k_lo[3];       // lowest voxel index per axis (floor(min / v))
+  int nvox[3];       // voxels per axis
+  int dims[3];       // cells per axis = nvox * m
+  long long ncells;
+  long long nvoxels;
+};
+
+struct Cloud {
+  long long n = 0;
+  double *d_xyz = nullptr;      // caller order, fp64 AoS
+  bool owned = false;
+  long long cap_xyz = 0;
+  bool grid_valid = false;
+  double bbox_min[3], bbox_max[3];
+  bool bbox_valid = false;
+  Lattice lat;
+  P4 *d_sorted = nullptr;       // cell-sorted points
+  long long cap_sorted = 0;
+  uint32_t *d_cell_off = nullptr;   // ncells + 1 CSR offsets into d_sorted: cell c = [off[c], off[c+1])
+  long long cap_cells = 0;
+  uint32_t *d_cell_id = nullptr;    // scratch: cell of each point (caller order)
+  long long cap_cell_id = 0;
+  // per-query results, SORTED order of this cloud (unsorted on demand)
+  int32_t *d_nn_idx = nullptr;      // nearest neighbour in the other cloud (caller index there)
+  double *d_nn_d2 = nullptr;
+  long long cap_nn = 0, cap_nn_d2 = 0;
+  bool nn_valid = false;
+  double *d_entropy = nullptr;
+  long long cap_entropy = 0;
+  bool entropy_valid = false;
+};
+
+}  // namespace me
+
+struct me_ctx {
+  int device = 0;
+  int rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  double nn_cell_size = 0.0;
+  long long max_grid_cells = 1ll << 28;
+  double voxel_hint = 0.0;          // lattice alignment requested by the voxel stage
+  me::Cloud cloud[2];
+  // small device scratch for reductions / accumulators
+  void *d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void *h_pinned = nullptr;         // pinned host mirror of the scratch
+  // large device scratch (scan partials, far list, voxel tables)
+  void *d_work = nullptr;
+  size_t work_bytes = 0;
+  cudaEvent_t ev[2 * ME_N_STAGE_TIMES];
+  bool ev_used[ME_N_STAGE_TIMES];
+  int sm_count = 148;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace me {
+
+int fail(me_ctx *ctx, int code, const std::string &msg);
+int ensure(me_ctx *ctx, void **ptr, long long *cap, long long need, size_t elem);
+int ensure_work(me_ctx *ctx, size_t bytes);
+
+#define ME_CUDA(ctx, call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return me::fail((ctx), ME_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+  } while (0)
+
+#define ME_TRY(expr)                \
+  do {                              \
+    int rc__ = (expr);              \
+    if (rc__ != ME_OK) return rc__; \
+  } while (0)
+
+#define ME_LAUNCH_CHECK(ctx)                                                                       \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return me::fail((ctx), ME_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+// contiguous query range of this rank (sorted order of the query cloud)
+inline void shard_range(const me_ctx *ctx, long long n, long long *b, long long *e) {
+  *b = n * ctx->rank / ctx->world;
+  *e = n * (ctx->rank + 1) / ctx->world;
+}
+
+struct StageTimer {
+  me_ctx *ctx; int stage;
+  StageTimer(me_ctx *c, int s) : ctx(c), stage(s) { cudaEventRecord(c->ev[2 * s], c->stream); }
+  ~StageTimer() { cudaEventRecord(ctx->ev[2 * stage + 1], ctx->stream); ctx->ev_used[stage] = true; }
+};
+
+// stage entry points (implemented in grid.cu / nn.cu / mme.cu / voxel.cu)
+int compute_bbox(me_ctx *ctx, int which);
+int build_grid(me_ctx *ctx, int which);
+int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e);
+int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2);
+int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out);
+int unsort_entropy(me_ctx *ctx, int which, double *h_entropy);
+int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
+            double **rows27);
+int transform_cloud(me_ctx *ctx, int which, const double T[16]);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+
+// squared distance exactly as nanoflann's L2_Adaptor accumulates it: ((dx*dx) + dy*dy) + dz*dz, no contraction
+__device__ __forceinline__ double d2_kd(double ax, double ay, double az, double bx, double by, double bz) {
+  double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+// Eigen fixed-size squaredNorm: x*x + (y*y + z*z)
+__device__ __forceinline__ double sqnorm_eigen(double dx, double dy, double dz) {
+  return __dadd_rn(__dmul_rn(dx, dx), __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dz, dz)));
+}
+
+// lattice coordinate of one axis: voxel index floor(x / v) (IEEE division, as the reference) and the cell inside it
+__device__ __forceinline__ long long cell_coord(double x, const Lattice &L, int axis) {
+  double kf = floor(__ddiv_rn(x, L.v));
+  double fx = __dsub_rn(x, __dmul_rn(kf, L.v));
+  int s = (int)floor(fx * L.m_over_v);
+  s = s < 0 ? 0 : (s >= L.m ? L.m - 1 : s);
+  // clamp far-away queries before the integer conversion can overflow
+  double kk = kf - (double)L.k_lo[axis];
+  if (kk < -4.0e9) kk = -4.0e9;
+  if (kk > 4.0e9) kk = 4.0e9;
+  return (long long)kk * L.m + s;
+}
+// continuous cell coordinate (for face distances)
+__device__ __forceinline__ double cell_coord_cont(double x, const Lattice &L, int axis) {
+  return (x - (double)L.k_lo[axis] * L.v) / L.h;
+}
+
+__device__ __forceinline__ P4 load_p4(const P4 *p) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  double2 a = __ldg(q), b = __ldg(q + 1);
+  P4 r;
+  r.x = a.x; r.y = a.y; r.z = b.x; r.idx = __double_as_longlong(b.y);
+  return r;
+}
+
+// order-preserving map double -> uint64 (for atomicMin/atomicMax on doubles)
+__device__ __host__ __forceinline__ unsigned long long enc_ordered(double d) {
+#ifdef __CUDA_ARCH__
+  unsigned long long u = (unsigned long long)__double_as_longlong(d);
+#else
+  unsigned long long u; memcpy(&u, &d, 8);
+#endif
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __host__ __forceinline__ double dec_ordered(unsigned long long u) {
+  u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Eigen 3x3 determinant (cofactor expansion, bruteforce_det3_helper); m row-major
+__device__ __forceinline__ double det3(const double *m) {
+  double a = m[0] * (m[4] * m[8] - m[5] * m[7]);
+  double b = m[1] * (m[3] * m[8] - m[5] * m[6]);
+  double c = m[2] * (m[3] * m[7] - m[4] * m[6]);
+  return a - b + c;
+}
+
+}  // namespace me

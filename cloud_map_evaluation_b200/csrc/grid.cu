@@ -1,0 +1,362 @@
+// grid.cu — lays a cloud out once into a dense, voxel-aligned, cell-sorted lattice in HBM.
+//
+//   bbox reduce -> lattice choice (host) -> cell histogram -> in-place exclusive scan -> scatter (counting sort)
+//
+// The layout replaces the reference's per-call KD-tree builds (open3d::geometry::KDTreeFlann::SetGeometry,
+// map_eval.cpp:1213-1214,1226-1227,1401-1402,1448-1449,1550-1551,1618-1619) and its std::unordered_map voxel
+// hashing (voxel_calculator.cpp:21-56).  All kernels here are HBM-streaming integer/byte work: coalesced loads,
+// grids sized in multiples of the SM count, no tensor cores.
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace me {
+
+static constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------------
+// bbox: min/max per axis + count of non-finite coordinates
+// scratch layout (uint64): [0..2] min xyz (ordered encoding), [3..5] max xyz, [6] non-finite count
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void bbox_init_kernel(unsigned long long *s) {
+  int t = threadIdx.x;
+  if (t < 3) s[t] = 0xffffffffffffffffull;
+  else if (t < 6) s[t] = 0ull;
+  else if (t == 6) s[t] = 0ull;
+}
+
+__global__ void __launch_bounds__(kThreads) bbox_kernel(const double *__restrict__ xyz, long long n,
+                                                        unsigned long long *__restrict__ s) {
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  unsigned long long bad = 0;
+  long long total = 3 * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    double v = __ldg(xyz + i);
+    int a = (int)(i % 3);
+    if (!isfinite(v)) { bad++; continue; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (a == k) { mn[k] = fmin(mn[k], v); mx[k] = fmax(mx[k], v); }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+  bad = (unsigned long long)warp_sum_ll((long long)bad);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (mn[k] <= mx[k]) {
+        atomicMin(s + k, enc_ordered(mn[k]));
+        atomicMax(s + 3 + k, enc_ordered(mx[k]));
+      }
+    }
+    if (bad) atomicAdd(s + 6, bad);
+  }
+}
+
+int compute_bbox(me_ctx *ctx, int which) {
+  Cloud &c = ctx->cloud[which];
+  if (c.bbox_valid) return ME_OK;
+  if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
+  unsigned long long *s = (unsigned long long *)ctx->d_scratch;
+  bbox_init_kernel<<<1, 32, 0, ctx->stream>>>(s);
+  ME_LAUNCH_CHECK(ctx);
+  int blocks = (int)std::min<long long>((3 * c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  bbox_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, s);
+  ME_LAUNCH_CHECK(ctx);
+  unsigned long long *h = (unsigned long long *)ctx->h_pinned;
+  ME_CUDA(ctx, cudaMemcpyAsync(h, s, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[6] != 0)
+    return fail(ctx, ME_ERR_RANGE, "cloud holds non-finite coordinates (the reference drops them at load, map_eval.cpp:6)");
+  for (int k = 0; k < 3; ++k) { c.bbox_min[k] = dec_ordered(h[k]); c.bbox_max[k] = dec_ordered(h[3 + k]); }
+  c.bbox_valid = true;
+  return ME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cell histogram
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) cell_count_kernel(const double *__restrict__ xyz, long long n, Lattice L,
+                                                              uint32_t *__restrict__ cell_id,
+                                                              uint32_t *__restrict__ count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    long long ix = cell_coord(x, L, 0), iy = cell_coord(y, L, 1), iz = cell_coord(z, L, 2);
+    // points define the lattice, so the coordinates are in range by construction; clamp against surprises
+    ix = ix < 0 ? 0 : (ix >= L.dims[0] ? L.dims[0] - 1 : ix);
+    iy = iy < 0 ? 0 : (iy >= L.dims[1] ? L.dims[1] - 1 : iy);
+    iz = iz < 0 ? 0 : (iz >= L.dims[2] ? L.dims[2] - 1 : iz);
+    long long c = (iz * L.dims[1] + iy) * (long long)L.dims[0] + ix;
+    cell_id[i] = (uint32_t)c;
+    atomicAdd(count + c, 1u);
+  }
+}
+
+// occupancy statistics of the histogram: [0] occupied cells, [1] max count
+__global__ void __launch_bounds__(kThreads) occupancy_kernel(const uint32_t *__restrict__ count, long long ncells,
+                                                             unsigned long long *__restrict__ stats) {
+  unsigned long long occ = 0, mx = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncells;
+       i += (long long)gridDim.x * blockDim.x) {
+    uint32_t c = __ldg(count + i);
+    occ += c != 0;
+    mx = c > mx ? c : mx;
+  }
+  occ = (unsigned long long)warp_sum_ll((long long)occ);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(stats, occ); atomicMax(stats + 1, mx); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// in-place exclusive scan over the cell counts (3 phases: tile sums, scan of tile sums, tile scan + offset)
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kScanItems = 8;                       // per thread
+static constexpr int kScanTile = kThreads * kScanItems;    // 2048 cells per block
+
+__global__ void __launch_bounds__(kThreads) scan_tile_sum_kernel(const uint32_t *__restrict__ a, long long n,
+                                                                 uint32_t *__restrict__ tile_sum) {
+  __shared__ uint32_t ws[kThreads / 32];
+  long long base = (long long)blockIdx.x * kScanTile;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    long long i = base + (long long)k * kThreads + threadIdx.x;
+    if (i < n) s += __ldg(a + i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += ws[w];
+    tile_sum[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of the tile sums, in place
+__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(uint32_t *__restrict__ tile_sum, long long ntiles) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (long long base = 0; base < ntiles; base += 1024) {
+    long long i = base + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sum[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = ws[threadIdx.x];
+      uint32_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (threadIdx.x >= o) winc += t; }
+      ws[threadIdx.x] = winc - w;   // exclusive prefix of warp sums
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    uint32_t excl = carry + ws[threadIdx.x >> 5] + inc - v;
+    if (i < ntiles) tile_sum[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+
+// per tile: exclusive scan + tile offset, written in place (count[c] -> start[c])
+__global__ void __launch_bounds__(kThreads) scan_apply_kernel(uint32_t *__restrict__ a, long long n,
+                                                              const uint32_t *__restrict__ tile_off) {
+  __shared__ uint32_t ws[kThreads / 32];
+  long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { long long i = base + k; v[k] = i < n ? a[i] : 0u; s += v[k]; }
+  uint32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += ws[w];
+  uint32_t run = tile_off[blockIdx.x] + woff + inc - s;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { long long i = base + k; if (i < n) a[i] = run; run += v[k]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// scatter: slot = start[c]++ on off[c+1]; afterwards off[c+1] = end of cell c = start of cell c+1 (CSR)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) scatter_kernel(const double *__restrict__ xyz, long long n,
+                                                           const uint32_t *__restrict__ cell_id,
+                                                           uint32_t *__restrict__ cell_cursor,
+                                                           P4 *__restrict__ sorted) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t c = __ldg(cell_id + i);
+    uint32_t slot = atomicAdd(cell_cursor + c, 1u);
+    double x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    double2 *o = reinterpret_cast<double2 *>(sorted + slot);
+    o[0] = make_double2(x, y);
+    o[1] = make_double2(z, __longlong_as_double(i));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: lattice choice
+// ---------------------------------------------------------------------------------------------------------------
+static bool make_lattice(const Cloud &c, double v, int m, long long budget, Lattice *out) {
+  Lattice L;
+  L.v = v; L.m = m; L.h = v / m; L.m_over_v = m / v;
+  long long nc = 1, nv = 1;
+  for (int a = 0; a < 3; ++a) {
+    double klo = std::floor(c.bbox_min[a] / v), khi = std::floor(c.bbox_max[a] / v);
+    if (!(klo > -2.0e9 && khi < 2.0e9)) return false;   // the reference casts to int (voxel_calculator.cpp:242)
+    L.k_lo[a] = (int)klo;
+    double nvx = khi - klo + 1.0;
+    if (nvx * m > 2.0e9) return false;
+    L.nvox[a] = (int)nvx;
+    L.dims[a] = L.nvox[a] * m;
+    if ((double)nc * L.dims[a] > 4.0e9) return false;
+    nc *= L.dims[a];
+    nv *= L.nvox[a];
+  }
+  if (nc > budget || nc >= 0xffffffffll) return false;
+  L.ncells = nc; L.nvoxels = nv;
+  *out = L;
+  return true;
+}
+
+static int histogram(me_ctx *ctx, Cloud &c, const Lattice &L) {
+  ME_TRY(ensure(ctx, (void **)&c.d_cell_off, &c.cap_cells, L.ncells + 1, sizeof(uint32_t)));
+  ME_TRY(ensure(ctx, (void **)&c.d_cell_id, &c.cap_cell_id, c.n, sizeof(uint32_t)));
+  // counts live at off[1..ncells]; off[0] stays 0, so after scan + scatter off[] is a CSR offset array
+  ME_CUDA(ctx, cudaMemsetAsync(c.d_cell_off, 0, (size_t)(L.ncells + 1) * sizeof(uint32_t), ctx->stream));
+  int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  cell_count_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, L, c.d_cell_id, c.d_cell_off + 1);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
+static int occupancy(me_ctx *ctx, Cloud &c, const Lattice &L, long long *occupied, long long *max_count) {
+  unsigned long long *s = (unsigned long long *)ctx->d_scratch;
+  ME_CUDA(ctx, cudaMemsetAsync(s, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  int blocks = (int)std::min<long long>((L.ncells + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  occupancy_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, s);
+  ME_LAUNCH_CHECK(ctx);
+  unsigned long long *h = (unsigned long long *)ctx->h_pinned;
+  ME_CUDA(ctx, cudaMemcpyAsync(h, s, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *occupied = (long long)h[0]; *max_count = (long long)h[1];
+  return ME_OK;
+}
+
+int build_grid(me_ctx *ctx, int which) {
+  Cloud &c = ctx->cloud[which];
+  if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
+  if (c.n >= 0x7fffffffll) return fail(ctx, ME_ERR_RANGE, "more than 2^31-1 points per cloud (the reference indexes with int)");
+  if (c.grid_valid) return ME_OK;
+  StageTimer timer(ctx, which == ME_CLOUD_EST ? 0 : 1);
+  ME_TRY(compute_bbox(ctx, which));
+
+  const long long budget = ctx->max_grid_cells;
+  double ext[3], vol = 1.0, ext_max = 0.0;
+  for (int a = 0; a < 3; ++a) { ext[a] = c.bbox_max[a] - c.bbox_min[a]; ext_max = std::max(ext_max, ext[a]); }
+  if (ext_max <= 0.0) ext_max = 1.0;
+  for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * ext_max);
+
+  // target edge: ~2 points per cell for a volume-filling cloud; refined below from the measured occupancy
+  double h_target = ctx->nn_cell_size > 0 ? ctx->nn_cell_size : std::cbrt(2.0 * vol / (double)c.n);
+  const double v_req = ctx->voxel_hint;
+  Lattice L;
+  bool have = false;
+  for (int iter = 0; iter < 4; ++iter) {
+    // pick (v, m): aligned to the voxel size when one is known, free otherwise
+    bool ok = false;
+    Lattice cand;
+    if (v_req > 0) {
+      int m = (int)std::max(1.0, std::floor(v_req / h_target + 0.5));
+      m = std::min(m, 1 << 20);
+      for (; m >= 1; --m) {
+        if (make_lattice(c, v_req, m, budget, &cand)) { ok = true; break; }
+        if (m > 64) m = (int)(m * 0.8);   // far over budget: shrink geometrically
+      }
+      if (!ok)
+        return fail(ctx, ME_ERR_RANGE, "voxel size too small for the dense lattice budget (raise max_grid_cells)");
+    } else {
+      double h = h_target;
+      for (int t = 0; t < 64 && !ok; ++t) { ok = make_lattice(c, h, 1, budget, &cand); if (!ok) h *= 1.26; }
+      if (!ok) return fail(ctx, ME_ERR_RANGE, "cannot fit the cloud into the dense lattice budget");
+    }
+    if (have && cand.ncells == L.ncells && cand.m == L.m && cand.v == L.v) break;  // refinement changed nothing
+    L = cand; have = true;
+    ME_TRY(histogram(ctx, c, L));
+    if (ctx->nn_cell_size > 0) break;   // caller fixed the cell size
+    long long occupied = 0, max_count = 0;
+    ME_TRY(occupancy(ctx, c, L, &occupied, &max_count));
+    double mean_occ = (double)c.n / (double)std::max<long long>(1, occupied);
+    if (mean_occ <= 4.0 || iter == 3) break;
+    // surface-like data: occupancy of occupied cells scales ~h^2; aim at ~2 points per occupied cell
+    double shrink = std::sqrt(2.0 / mean_occ);
+    double h_new = std::max(L.h * shrink, L.h * 0.25);
+    if (h_new >= 0.9 * L.h) break;
+    h_target = h_new;
+  }
+  c.lat = L;
+
+  // exclusive scan of the histogram, in place
+  long long ntiles = (L.ncells + kScanTile - 1) / kScanTile;
+  ME_TRY(ensure_work(ctx, (size_t)ntiles * sizeof(uint32_t)));
+  uint32_t *tile = (uint32_t *)ctx->d_work;
+  scan_tile_sum_kernel<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, tile);
+  ME_LAUNCH_CHECK(ctx);
+  scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(tile, ntiles);
+  ME_LAUNCH_CHECK(ctx);
+  scan_apply_kernel<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, tile);
+  ME_LAUNCH_CHECK(ctx);
+
+  ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, c.n, sizeof(P4)));
+  int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
+  ME_LAUNCH_CHECK(ctx);
+  c.grid_valid = true;
+  c.nn_valid = false;
+  c.entropy_valid = false;
+  return ME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Open3D PointCloud::Transform (map_eval.cpp:1206): p' = (T [p,1]).head<3>() / w, in place on the caller-order array
+// ---------------------------------------------------------------------------------------------------------------
+struct Mat16 { double t[16]; };
+__global__ void __launch_bounds__(kThreads) transform_kernel(double *__restrict__ xyz, long long n, Mat16 T) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2], o[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      o[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.t[r * 4], x), __dmul_rn(T.t[r * 4 + 1], y)),
+                                 __dmul_rn(T.t[r * 4 + 2], z)), T.t[r * 4 + 3]);
+    xyz[3 * i] = __ddiv_rn(o[0], o[3]);
+    xyz[3 * i + 1] = __ddiv_rn(o[1], o[3]);
+    xyz[3 * i + 2] = __ddiv_rn(o[2], o[3]);
+  }
+}
+
+int transform_cloud(me_ctx *ctx, int which, const double T[16]) {
+  Cloud &c = ctx->cloud[which];
+  if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
+  if (!c.owned) return fail(ctx, ME_ERR_INVALID, "me_transform needs a library-owned cloud (use me_set_cloud)");
+  Mat16 M;
+  std::memcpy(M.t, T, sizeof(M.t));
+  int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  transform_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, M);
+  ME_LAUNCH_CHECK(ctx);
+  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false;
+  return ME_OK;
+}
+
+}  // namespace me

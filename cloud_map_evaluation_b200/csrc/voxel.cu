@@ -1,0 +1,414 @@
+// voxel.cu — voxel Gaussians, voxel-pair Wasserstein distance (AWD / "VMD") and spatial consistency score (SCS).
+//
+// Replaces (reference):
+//   voxel_calculator.cpp:21-56    VoxelCalculator::buildVoxelMap   (sequential Welford into an unordered_map)
+//   voxel_calculator.cpp:97-113   computeVoxelEntropy              (second division by n-1)
+//   voxel_calculator.cpp:142-172  updateVoxelMap(const VoxelMap&)  (active / old / new labelling)
+//   voxel_calculator.cpp:115-140  computeWassersteinDistanceGaussian (third division, eigen-clamp, Cholesky trace)
+//   voxel_calculator.cpp:7-19     getNeighborIndices
+//   map_eval.cpp:240-390          MapEval::calculateVMD            (pair filter >= 100 points, mean, SCS)
+//
+// The lattice cells are sub-cells of the reference's voxels floor(x / v) (see Lattice in common.cuh), so a voxel is
+// m x m contiguous x-runs of the cell-sorted cloud: one warp reduces one voxel with no hashing and no atomics, and
+// est/gt voxels pair up by index arithmetic.  Moments are taken about the voxel centre in fp64
+// (mu = c + S1/n, M2 = S2 - S1 S1^T / n), which equals the Welford result to rounding.
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+
+namespace me {
+
+static constexpr int kThreads = 256;
+
+// ---- per-voxel moments -----------------------------------------------------------------------------------------
+// out: cnt[nvoxels] (int32), mom[nvoxels * 9] = S1(3), S2(xx,xy,xz,yy,yz,zz) about the voxel centre
+__global__ void __launch_bounds__(kThreads)
+voxel_moments_kernel(const P4 *__restrict__ S, const uint32_t *__restrict__ cell_off, Lattice L,
+                     int32_t *__restrict__ cnt, double *__restrict__ mom, unsigned long long *__restrict__ n_occupied) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int m = L.m;
+  unsigned long long occ = 0;
+  for (long long vox = warp; vox < L.nvoxels; vox += nwarps) {
+    const int vx = (int)(vox % L.nvox[0]);
+    const int vy = (int)((vox / L.nvox[0]) % L.nvox[1]);
+    const int vz = (int)(vox / ((long long)L.nvox[0] * L.nvox[1]));
+    const double cx = ((double)(L.k_lo[0] + vx) + 0.5) * L.v, cy = ((double)(L.k_lo[1] + vy) + 0.5) * L.v,
+                 cz = ((double)(L.k_lo[2] + vz) + 0.5) * L.v;
+    double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int n = 0;
+    for (int t = lane; t < m * m; t += 32) {
+      const long long z = (long long)vz * m + t / m, y = (long long)vy * m + t % m;
+      const long long row = (z * L.dims[1] + y) * (long long)L.dims[0] + (long long)vx * m;
+      const uint32_t b = __ldg(cell_off + row), e = __ldg(cell_off + row + m);
+      for (uint32_t j = b; j < e; ++j) {
+        const P4 p = load_p4(S + j);
+        const double dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+        n++;
+        s[0] += dx; s[1] += dy; s[2] += dz;
+        s[3] += dx * dx; s[4] += dx * dy; s[5] += dx * dz; s[6] += dy * dy; s[7] += dy * dz; s[8] += dz * dz;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = warp_sum(s[k]);
+    if (lane == 0) {
+      cnt[vox] = n;
+      if (n > 0) {
+        occ++;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) mom[vox * 9 + k] = s[k];
+      }
+    }
+  }
+  if (lane == 0 && occ) atomicAdd(n_occupied, occ);
+}
+
+// ---- 3x3 algebra (fp64) ---------------------------------------------------------------------------------------
+__device__ void eig3_jacobi(const double *a_in, double *w, double *v) {
+  double a[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { a[i] = a_in[i]; v[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    const double diag = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (off <= 1e-34 * diag || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[p * 3 + q];
+        if (apq == 0.0) continue;
+        const double app = a[p * 3 + p], aqq = a[q * 3 + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k * 3 + p], akq = a[k * 3 + q];
+          a[k * 3 + p] = c * akp - s * akq;
+          a[k * 3 + q] = s * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+          a[p * 3 + k] = c * apk - s * aqk;
+          a[q * 3 + k] = s * apk + c * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+          v[k * 3 + p] = c * vkp - s * vkq;
+          v[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w[0] = a[0]; w[1] = a[4]; w[2] = a[8];
+}
+
+// Eigen LLT (unblocked, lower, in place); stops at the first non-positive pivot leaving the rest untouched
+__device__ void llt3_inplace(double *m) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double x = m[k * 3 + k];
+    for (int j = 0; j < k; ++j) x -= m[k * 3 + j] * m[k * 3 + j];
+    if (x <= 0.0) return;
+    x = sqrt(x);
+    m[k * 3 + k] = x;
+    for (int i = k + 1; i < 3; ++i) {
+      double s = m[i * 3 + k];
+      for (int j = 0; j < k; ++j) s -= m[i * 3 + j] * m[k * 3 + j];
+      m[i * 3 + k] = s / x;
+    }
+  }
+}
+
+// voxel_calculator.cpp:118-125: sigma / (n - 1), symmetrise, clamp eigenvalues at 1e-6
+__device__ void clamp_cov(const double *stored, int n, double *out) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (n > 1) {
+    double s[9], sym[9], w[3], v[9];
+    const double nm1 = (double)(n - 1);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s[i] = stored[i] / nm1;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sym[r * 3 + c] = (s[r * 3 + c] + s[c * 3 + r]) / 2;
+    eig3_jacobi(sym, w, v);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k] = fmax(w[k], 1e-6);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc += v[r * 3 + k] * w[k] * v[c * 3 + k];
+        out[r * 3 + c] = acc;
+      }
+  }
+}
+
+// voxel_calculator.cpp:115-140, arguments in the reference's call order (voxel1 = gt, voxel2 = est; map_eval.cpp:284)
+__device__ double wasserstein(const double *mu1, const double *sig1, int n1, const double *mu2, const double *sig2, int n2) {
+  double s1[9], s2[9], l1[9], tmp[9], a[9];
+  clamp_cov(sig1, n1, s1);
+  clamp_cov(sig2, n2, s2);
+  const double dm0 = mu1[0] - mu2[0], dm1 = mu1[1] - mu2[1], dm2 = mu1[2] - mu2[2];
+  const double tr_sum = (s1[0] + s2[0]) + (s1[4] + s2[4]) + (s1[8] + s2[8]);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) l1[i] = s1[i];
+  llt3_inplace(l1);
+  l1[1] = l1[2] = l1[5] = 0.0;                       // matrixL(): lower triangular view
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s += l1[i * 3 + k] * s2[k * 3 + j];
+      tmp[i * 3 + j] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s += tmp[i * 3 + k] * l1[j * 3 + k];   // * L1^T
+      a[i * 3 + j] = s;
+    }
+  llt3_inplace(a);
+  const double tr_sqrt = a[0] + a[4] + a[8];
+  const double dist = (dm0 * dm0 + dm1 * dm1 + dm2 * dm2) + tr_sum - 2 * tr_sqrt;
+  return sqrt(fmax(0.0, dist));
+}
+
+// mu and the sigma the reference has stored after buildVoxelMap: M2 for n <= 10 (voxel_calculator.cpp:47),
+// (M2 / (n-1)) / (n-1) otherwise (:48 then :102)
+__device__ void stored_gaussian(const double *mom, int n, double cx, double cy, double cz, double *mu, double *sig) {
+  const double nd = (double)n;
+  mu[0] = cx + mom[0] / nd; mu[1] = cy + mom[1] / nd; mu[2] = cz + mom[2] / nd;
+  double m2[6];
+  m2[0] = mom[3] - mom[0] * mom[0] / nd; m2[1] = mom[4] - mom[0] * mom[1] / nd; m2[2] = mom[5] - mom[0] * mom[2] / nd;
+  m2[3] = mom[6] - mom[1] * mom[1] / nd; m2[4] = mom[7] - mom[1] * mom[2] / nd; m2[5] = mom[8] - mom[2] * mom[2] / nd;
+  if (n > 10) {
+    const double nm1 = (double)(n - 1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m2[k] = (m2[k] / nm1) / nm1;
+  }
+  sig[0] = m2[0]; sig[1] = m2[1]; sig[2] = m2[2];
+  sig[3] = m2[1]; sig[4] = m2[3]; sig[5] = m2[4];
+  sig[6] = m2[2]; sig[7] = m2[4]; sig[8] = m2[5];
+}
+
+struct AwdAcc {
+  unsigned long long n_pairs, n_active, n_new, n_scs;
+  double sum_w, sum_scs;
+};
+
+// ---- pairing + Wasserstein: one thread per est voxel -----------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+awd_kernel(Lattice Le, Lattice Lg, const int32_t *__restrict__ cnt_e, const double *__restrict__ mom_e,
+           const int32_t *__restrict__ cnt_g, const double *__restrict__ mom_g, int min_points,
+           double *__restrict__ w_out, uint32_t *__restrict__ pair_list, double *__restrict__ rows27,
+           AwdAcc *__restrict__ acc) {
+  unsigned long long l_active = 0, l_new = 0;
+  for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < Le.nvoxels;
+       vox += (long long)gridDim.x * blockDim.x) {
+    double w = NAN;
+    const int ne = cnt_e[vox];
+    if (ne > 0) {
+      const int vx = (int)(vox % Le.nvox[0]);
+      const int vy = (int)((vox / Le.nvox[0]) % Le.nvox[1]);
+      const int vz = (int)(vox / ((long long)Le.nvox[0] * Le.nvox[1]));
+      const long long kx = (long long)Le.k_lo[0] + vx, ky = (long long)Le.k_lo[1] + vy, kz = (long long)Le.k_lo[2] + vz;
+      const long long gx = kx - Lg.k_lo[0], gy = ky - Lg.k_lo[1], gz = kz - Lg.k_lo[2];
+      int ng = 0;
+      long long gvox = -1;
+      if (gx >= 0 && gx < Lg.nvox[0] && gy >= 0 && gy < Lg.nvox[1] && gz >= 0 && gz < Lg.nvox[2]) {
+        gvox = (gz * Lg.nvox[1] + gy) * (long long)Lg.nvox[0] + gx;
+        ng = cnt_g[gvox];
+      }
+      if (ng > 0) l_active++; else l_new++;
+      if (ng > 0 && ne >= min_points && ng >= min_points) {       // map_eval.cpp:274-281
+        const double cx = ((double)kx + 0.5) * Le.v, cy = ((double)ky + 0.5) * Le.v, cz = ((double)kz + 0.5) * Le.v;
+        double mu_e[3], sig_e[9], mu_g[3], sig_g[9];
+        stored_gaussian(mom_e + vox * 9, ne, cx, cy, cz, mu_e, sig_e);
+        stored_gaussian(mom_g + gvox * 9, ng, cx, cy, cz, mu_g, sig_g);
+        w = wasserstein(mu_g, sig_g, ng, mu_e, sig_e, ne);         // (gt_voxel, est_voxel) map_eval.cpp:284
+        const unsigned long long slot = atomicAdd(&acc->n_pairs, 1ull);
+        pair_list[slot] = (uint32_t)vox;
+        atomicAdd(&acc->sum_w, w);
+        if (rows27) {                                              // map_eval.cpp:288-302
+          double *r = rows27 + slot * 27;
+          r[0] = (double)kx * Le.v; r[1] = (double)ky * Le.v; r[2] = (double)kz * Le.v;
+          r[3] = ((double)kx + 1.0) * Le.v; r[4] = ((double)ky + 1.0) * Le.v; r[5] = ((double)kz + 1.0) * Le.v;
+          r[6] = mu_e[0]; r[7] = mu_e[1]; r[8] = mu_e[2];
+          r[9] = w; r[10] = (double)ng; r[11] = (double)ne;
+          r[12] = sig_e[0]; r[13] = sig_e[1]; r[14] = sig_e[2]; r[15] = sig_e[4]; r[16] = sig_e[5]; r[17] = sig_e[8];
+          r[18] = mu_g[0]; r[19] = mu_g[1]; r[20] = mu_g[2];
+          r[21] = sig_g[0]; r[22] = sig_g[1]; r[23] = sig_g[2]; r[24] = sig_g[4]; r[25] = sig_g[5]; r[26] = sig_g[8];
+        }
+      }
+    }
+    w_out[vox] = w;
+  }
+  l_active = (unsigned long long)warp_sum_ll((long long)l_active);
+  l_new = (unsigned long long)warp_sum_ll((long long)l_new);
+  if ((threadIdx.x & 31) == 0) {
+    if (l_active) atomicAdd(&acc->n_active, l_active);
+    if (l_new) atomicAdd(&acc->n_new, l_new);
+  }
+}
+
+// ---- SCS: one warp per paired voxel, lanes over the (2R+1)^3 - 1 neighbour offsets (map_eval.cpp:351-387) -------
+__global__ void __launch_bounds__(kThreads)
+scs_kernel(Lattice Le, const double *__restrict__ w_vox, const uint32_t *__restrict__ pair_list, int radius,
+           AwdAcc *__restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned long long npairs = acc->n_pairs;
+  const int side = 2 * radius + 1, total = side * side * side;
+  double l_scs = 0.0;
+  unsigned long long l_cnt = 0;
+  for (long long pi = warp; pi < (long long)npairs; pi += nwarps) {
+    const long long vox = pair_list[pi];
+    const int vx = (int)(vox % Le.nvox[0]);
+    const int vy = (int)((vox / Le.nvox[0]) % Le.nvox[1]);
+    const int vz = (int)(vox / ((long long)Le.nvox[0] * Le.nvox[1]));
+    double sum = 0.0;
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      double mean = 0.0;
+      if (pass) { if (n == 0) break; mean = sum / (double)n; sum = 0.0; }
+      for (int t = lane; t < total; t += 32) {
+        const int dx = t / (side * side) - radius, dy = (t / side) % side - radius, dz = t % side - radius;
+        if (dx == 0 && dy == 0 && dz == 0) continue;
+        const int x = vx + dx, y = vy + dy, z = vz + dz;
+        if (x < 0 || x >= Le.nvox[0] || y < 0 || y >= Le.nvox[1] || z < 0 || z >= Le.nvox[2]) continue;
+        const double w = __ldg(w_vox + ((long long)z * Le.nvox[1] + y) * Le.nvox[0] + x);
+        if (isnan(w)) continue;
+        if (pass == 0) { sum += w; n++; } else sum += (w - mean) * (w - mean);
+      }
+      sum = warp_sum(sum);
+      if (pass == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+      } else if (lane == 0) {
+        const double var = sum / (double)n;
+        l_scs += sqrt(var) / mean;
+        l_cnt++;
+      }
+    }
+  }
+  if (lane == 0 && l_cnt) { atomicAdd(&acc->sum_scs, l_scs); atomicAdd(&acc->n_scs, l_cnt); }
+}
+
+__global__ void zero_awd_acc_kernel(AwdAcc *a, unsigned long long *occ2) {
+  a->n_pairs = a->n_active = a->n_new = a->n_scs = 0;
+  a->sum_w = a->sum_scs = 0.0;
+  occ2[0] = occ2[1] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
+            double **rows27) {
+  std::memset(out, 0, sizeof(*out));
+  if (n_rows) *n_rows = 0;
+  if (rows27) *rows27 = nullptr;
+  if (!(voxel_size > 0)) return fail(ctx, ME_ERR_INVALID, "vmd_voxel_size must be > 0");
+  if (scs_radius < 0 || scs_radius > 64) return fail(ctx, ME_ERR_INVALID, "scs_radius out of range");
+  if (ctx->cloud[0].n <= 0 || ctx->cloud[1].n <= 0) return fail(ctx, ME_ERR_EMPTY, "both clouds must be set");
+  // the lattices must be aligned with this voxel size; rebuild them if they are not
+  for (int w = 0; w < 2; ++w) {
+    Cloud &c = ctx->cloud[w];
+    if (c.grid_valid && c.lat.v != voxel_size) c.grid_valid = false;
+  }
+  ctx->voxel_hint = voxel_size;
+  ME_TRY(build_grid(ctx, ME_CLOUD_EST));
+  ME_TRY(build_grid(ctx, ME_CLOUD_GT));
+  Cloud &E = ctx->cloud[ME_CLOUD_EST], &G = ctx->cloud[ME_CLOUD_GT];
+  const Lattice Le = E.lat, Lg = G.lat;
+  if (Le.nvoxels >= 0xffffffffll) return fail(ctx, ME_ERR_RANGE, "too many voxels");
+
+  // work layout: cnt_e | cnt_g | mom_e | mom_g | w_vox | pair_list | rows27
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o_cnt_e = 0;
+  size_t o_cnt_g = o_cnt_e + align((size_t)Le.nvoxels * sizeof(int32_t));
+  size_t o_mom_e = o_cnt_g + align((size_t)Lg.nvoxels * sizeof(int32_t));
+  size_t o_mom_g = o_mom_e + align((size_t)Le.nvoxels * 9 * sizeof(double));
+  size_t o_w = o_mom_g + align((size_t)Lg.nvoxels * 9 * sizeof(double));
+  size_t o_pairs = o_w + align((size_t)Le.nvoxels * sizeof(double));
+  size_t o_rows = o_pairs + align((size_t)Le.nvoxels * sizeof(uint32_t));
+  // a voxel pair needs >= min_points points in each cloud, which bounds the number of rows
+  long long max_pairs = std::min<long long>(Le.nvoxels, std::min(E.n, G.n) / std::max(1, min_points) + 1);
+  size_t total = o_rows + (rows27 ? align((size_t)max_pairs * 27 * sizeof(double)) : 0);
+  ME_TRY(ensure_work(ctx, total));
+  char *base = (char *)ctx->d_work;
+  int32_t *cnt_e = (int32_t *)(base + o_cnt_e), *cnt_g = (int32_t *)(base + o_cnt_g);
+  double *mom_e = (double *)(base + o_mom_e), *mom_g = (double *)(base + o_mom_g);
+  double *w_vox = (double *)(base + o_w);
+  uint32_t *pair_list = (uint32_t *)(base + o_pairs);
+  double *d_rows = rows27 ? (double *)(base + o_rows) : nullptr;
+
+  AwdAcc *acc = (AwdAcc *)ctx->d_scratch;
+  unsigned long long *occ = (unsigned long long *)((char *)ctx->d_scratch + 256);
+  zero_awd_acc_kernel<<<1, 1, 0, ctx->stream>>>(acc, occ);
+  ME_LAUNCH_CHECK(ctx);
+  {
+    StageTimer timer(ctx, 6);
+    int blocks_e = (int)std::min<long long>((Le.nvoxels * 32 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
+    voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, E.d_cell_off, Le, cnt_e, mom_e, occ);
+    ME_LAUNCH_CHECK(ctx);
+    int blocks_g = (int)std::min<long long>((Lg.nvoxels * 32 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
+    voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, G.d_cell_off, Lg, cnt_g, mom_g, occ + 1);
+    ME_LAUNCH_CHECK(ctx);
+  }
+  {
+    StageTimer timer(ctx, 7);
+    int blocks = (int)std::min<long long>((Le.nvoxels + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
+    awd_kernel<<<std::max(1, blocks), kThreads, 0, ctx->stream>>>(Le, Lg, cnt_e, mom_e, cnt_g, mom_g, min_points, w_vox,
+                                                                 pair_list, d_rows, acc);
+    ME_LAUNCH_CHECK(ctx);
+  }
+  {
+    StageTimer timer(ctx, 8);
+    scs_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
+    ME_LAUNCH_CHECK(ctx);
+  }
+  struct Host { AwdAcc a; char pad[256 - sizeof(AwdAcc)]; unsigned long long occ[2]; };
+  Host *h = (Host *)ctx->h_pinned;
+  ME_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch, sizeof(Host), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out->n_pairs = (int64_t)h->a.n_pairs;
+  out->n_scs = (int64_t)h->a.n_scs;
+  out->n_voxels_est = (int64_t)h->occ[0];
+  out->n_voxels_gt = (int64_t)h->occ[1];
+  out->n_active = (int64_t)h->a.n_active;
+  out->n_new = (int64_t)h->a.n_new;
+  out->n_old = out->n_voxels_gt - out->n_active;
+  out->awd = h->a.sum_w / (double)h->a.n_pairs;        // 0/0 -> NaN as map_eval.cpp:324
+  out->scs = h->a.sum_scs / (double)h->a.n_scs;        // map_eval.cpp:387
+  if (n_rows) *n_rows = out->n_pairs;
+  if (rows27) {
+    size_t bytes = (size_t)std::max<int64_t>(out->n_pairs, 1) * 27 * sizeof(double);
+    double *hr = (double *)std::malloc(bytes);
+    if (!hr) return fail(ctx, ME_ERR_NOMEM, "malloc(rows27) failed");
+    if (out->n_pairs > 0) {
+      ME_CUDA(ctx, cudaMemcpyAsync(hr, d_rows, (size_t)out->n_pairs * 27 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *rows27 = hr;
+  }
+  return ME_OK;
+}
+
+}  // namespace me

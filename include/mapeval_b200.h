@@ -32,6 +32,12 @@ extern "C" {
 
 #define ME_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define ME_API __attribute__((visibility("default")))
+#else
+#define ME_API
+#endif
+
 typedef enum {
   ME_OK = 0,
   ME_ERR_INVALID = -1,     /* bad argument / call order                       */
@@ -68,6 +74,8 @@ typedef struct {
   void   *stream;          /* cudaStream_t to launch on; NULL = library-owned stream       */
   double  nn_cell_size;    /* edge of the hashed-grid cells in metres; <= 0 = auto         */
   int64_t max_grid_cells;  /* budget for the dense cell table; <= 0 = default (2^28)       */
+  double  vmd_voxel_size;  /* voxel edge the lattices should align to (the config's vmd_voxel_size);
+                              <= 0 = unknown: me_eval_awd then re-lays the clouds out once     */
 } me_options;
 
 /* ---- a1/a2/a4: AC / COM / CD inlier statistics and full Chamfer ------------------------------- */
@@ -136,57 +144,57 @@ typedef struct {
 
 /* ---- lifecycle ---------------------------------------------------------------------------------- */
 
-int  me_abi_version(void);
-int  me_create(const me_options *opt, me_ctx **out);
-void me_destroy(me_ctx *ctx);
-const char *me_last_error(const me_ctx *ctx);      /* ctx may be NULL: last error of me_create on this thread */
-int  me_set_stream(me_ctx *ctx, void *cuda_stream);
-int  me_set_shard(me_ctx *ctx, int32_t rank, int32_t world);
-int  me_synchronize(me_ctx *ctx);
+ME_API int  me_abi_version(void);
+ME_API int  me_create(const me_options *opt, me_ctx **out);
+ME_API void me_destroy(me_ctx *ctx);
+ME_API const char *me_last_error(const me_ctx *ctx);      /* ctx may be NULL: last error of me_create on this thread */
+ME_API int  me_set_stream(me_ctx *ctx, void *cuda_stream);
+ME_API int  me_set_shard(me_ctx *ctx, int32_t rank, int32_t world);
+ME_API int  me_synchronize(me_ctx *ctx);
 
 /* replaces: io::ReadPointCloud* results held in map_3d_/gt_3d_ (map_eval.cpp:10-21) — the clouds the path reads.
  * me_set_cloud copies host memory (async on the stream; pinned memory makes it truly async);
  * me_set_cloud_device borrows an fp64 N x 3 device buffer that must outlive the context's use of it. */
-int  me_set_cloud(me_ctx *ctx, int which, const double *xyz_host, int64_t n);
-int  me_set_cloud_device(me_ctx *ctx, int which, const double *xyz_device, int64_t n);
+ME_API int  me_set_cloud(me_ctx *ctx, int which, const double *xyz_host, int64_t n);
+ME_API int  me_set_cloud_device(me_ctx *ctx, int which, const double *xyz_device, int64_t n);
 /* replaces: map_3d_->Transform(initial_matrix) (map_eval.cpp:1206); T is a row-major 4x4 */
-int  me_transform(me_ctx *ctx, int which, const double T[16]);
+ME_API int  me_transform(me_ctx *ctx, int which, const double T[16]);
 /* builds (or rebuilds) the cell-sorted grid of one cloud; the eval calls build lazily if needed */
-int  me_build_grid(me_ctx *ctx, int which);
+ME_API int  me_build_grid(me_ctx *ctx, int which);
 
 /* replaces: MapEval::calculateMetricsWithInitialMatrix (map_eval.cpp:1204-1260), getDiffRegResultWithCorrespondence
  * (:1069-1145), the metric half of calculateMetrics (:1147-1202) and computeChamferDistance (:1398-1431). */
-int  me_eval_nn_accum(me_ctx *ctx, const me_nn_params *p, me_nn_accum *est_to_gt, me_nn_accum *gt_to_est);
-int  me_nn_finalize(const me_nn_params *p, const me_nn_accum *est_to_gt, const me_nn_accum *gt_to_est,
+ME_API int  me_eval_nn_accum(me_ctx *ctx, const me_nn_params *p, me_nn_accum *est_to_gt, me_nn_accum *gt_to_est);
+ME_API int  me_nn_finalize(const me_nn_params *p, const me_nn_accum *est_to_gt, const me_nn_accum *gt_to_est,
                     int64_t n_est, int64_t n_gt, me_nn_result *out);      /* host only, no device work */
-int  me_eval_nn(me_ctx *ctx, const me_nn_params *p, me_nn_result *out);   /* accum + finalize, world must be 1 */
+ME_API int  me_eval_nn(me_ctx *ctx, const me_nn_params *p, me_nn_result *out);   /* accum + finalize, world must be 1 */
 /* per-query nearest neighbour of the last me_eval_nn*, original point order of the QUERY cloud;
  * which_query = ME_CLOUD_EST -> est->gt sweep.  Only this rank's query range is filled (others -1 / NaN). */
-int  me_get_nn(me_ctx *ctx, int which_query, int32_t *nn_index, double *nn_sqdist);
+ME_API int  me_get_nn(me_ctx *ctx, int which_query, int32_t *nn_index, double *nn_sqdist);
 
 /* replaces: ComputeMeanMapEntropyUsingNormalTBB / ...UsingNormal (min_neighbors 10, map_eval.cpp:1608-1737, 1538-1606),
  * ComputeMeanMapEntropy (min_neighbors 5, :1438-1535), ComputeEntropy (:1433-1436) and the min/max side effect of
  * ColorPointCloudByMME (:697-701).  entropies_host (nullable) receives N fp64, zeros where invalid. */
-int  me_eval_mme_accum(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_accum *out);
-int  me_mme_finalize(const me_mme_accum *acc, int64_t n_total, me_mme_result *out);   /* host only */
-int  me_eval_mme(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_result *out,
+ME_API int  me_eval_mme_accum(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_accum *out);
+ME_API int  me_mme_finalize(const me_mme_accum *acc, int64_t n_total, me_mme_result *out);   /* host only */
+ME_API int  me_eval_mme(me_ctx *ctx, int which, double radius, int32_t min_neighbors, me_mme_result *out,
                  double *entropies_host);
-int  me_get_entropies(me_ctx *ctx, int which, double *entropies_host);
+ME_API int  me_get_entropies(me_ctx *ctx, int which, double *entropies_host);
 
 /* replaces: MapEval::calculateVMD (map_eval.cpp:240-390) with VoxelCalculator::buildVoxelMap / computeVoxelEntropy /
  * updateVoxelMap / computeWassersteinDistanceGaussian / getNeighborIndices (voxel_calculator.cpp:7-56,97-172,241-245).
  * rows27 (nullable): library-allocated n_rows x 27 table = the columns of voxel_errors.txt (map_eval.cpp:292-302),
  * release with me_free.  Not sharded: every rank computes the whole (cheap) voxel stage. */
-int  me_eval_awd(me_ctx *ctx, double voxel_size, int32_t min_points, int32_t scs_radius, me_awd_result *out,
+ME_API int  me_eval_awd(me_ctx *ctx, double voxel_size, int32_t min_points, int32_t scs_radius, me_awd_result *out,
                  int64_t *n_rows, double **rows27);
-void me_free(void *p);
+ME_API void me_free(void *p);
 
 /* timing of the last call of each stage in milliseconds (CUDA events on the context's stream):
  * [0] grid est [1] grid gt [2] nn est->gt [3] nn gt->est [4] mme est [5] mme gt [6] voxel moments [7] awd [8] scs */
 #define ME_N_STAGE_TIMES 9
-int  me_get_stage_times(me_ctx *ctx, double ms[ME_N_STAGE_TIMES]);
+ME_API int  me_get_stage_times(me_ctx *ctx, double ms[ME_N_STAGE_TIMES]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
-int64_t me_launch_count(const me_ctx *ctx);
+ME_API int64_t me_launch_count(const me_ctx *ctx);
 
 #ifdef __cplusplus
 }

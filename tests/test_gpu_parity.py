@@ -1,0 +1,264 @@
+"""GPU parity: the sm_100a path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): integer counts bit-exact; AC/COM/CD/MME/AWD/SCS within 1e-5 relative.
+The tests assert a much tighter RTOL (fp64 arithmetic on both sides; only summation order differs)."""
+import numpy as np
+import pytest
+
+from cloud_map_evaluation_b200 import _abi as A
+from cloud_map_evaluation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_BAR = 1e-5     # the stated bar
+RTOL = 1e-9         # what we actually hold
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def api():
+    from cloud_map_evaluation_b200 import api as _api
+    return _api
+
+
+def _ctx(api, est, gt, **kw):
+    ctx = api.MapEvalB200(**kw)
+    ctx.set_cloud(A.ME_CLOUD_EST, est)
+    ctx.set_cloud(A.ME_CLOUD_GT, gt)
+    return ctx
+
+
+def _cmp_dir(got, exp):
+    assert got.n_source == exp.n_source
+    assert got.n_corr == exp.n_corr
+    assert list(got.n_inlier) == list(exp.n_inlier)
+    assert got.n_ub == exp.n_ub
+    for k in ("mean", "rmse", "fitness", "sigma"):
+        np.testing.assert_allclose(list(getattr(got, k)), list(getattr(exp, k)), rtol=RTOL, atol=1e-300, err_msg=k)
+    np.testing.assert_allclose(got.sum_nn_dist, exp.sum_nn_dist, rtol=RTOL)
+
+
+def _cmp_nn(got, exp):
+    _cmp_dir(got.est_to_gt, exp.est_to_gt)
+    _cmp_dir(got.gt_to_est, exp.gt_to_est)
+    for k in ("cd", "f1", "iou"):
+        np.testing.assert_allclose(list(getattr(got, k)), list(getattr(exp, k)), rtol=RTOL, equal_nan=True, err_msg=k)
+    np.testing.assert_allclose(got.full_cd, exp.full_cd, rtol=RTOL)
+
+
+@pytest.mark.parametrize("pairing", [A.ME_PAIRING_AS_WRITTEN, A.ME_PAIRING_GEOMETRIC])
+@pytest.mark.parametrize("cutoff", [A.ME_CUTOFF_SQDIST_LE_R, A.ME_CUTOFF_DIST_LT_R])
+def test_nn_c1_config(api, O, pairing, cutoff):
+    """BASELINE config C1: 100k vs 100k uniform box, AC + CD."""
+    est, gt, cfg = synth.make_pair("C1")
+    p = A.make_nn_params(cfg["tau"], 1.0, cutoff_mode=cutoff, pairing=pairing)
+    with _ctx(api, est, gt) as ctx:
+        got = ctx.calculateMetricsWithInitialMatrix(p)
+        idx_e, d2_e = ctx.get_nn(A.ME_CLOUD_EST)
+        idx_g, d2_g = ctx.get_nn(A.ME_CLOUD_GT)
+    exp, ie, ig = O.eval_nn(est, gt, p, want_indices=True)
+    _cmp_nn(got, exp)
+    np.testing.assert_array_equal(idx_e, ie)
+    np.testing.assert_array_equal(idx_g, ig)
+    oi, od2 = O.knn1(est, gt)
+    np.testing.assert_array_equal(d2_e, od2)      # squared distances are bit-identical
+
+
+def test_nn_small_cutoff_and_unequal_sizes(api, O):
+    side = synth.box_side_for_density(60000)
+    gt = synth.uniform_box(60000, side, 11)
+    est = synth.uniform_box(83211, side, 12, noise_sigma=0.02)
+    for pairing in (A.ME_PAIRING_AS_WRITTEN, A.ME_PAIRING_GEOMETRIC):
+        p = A.make_nn_params([0.2, 0.1, 0.08, 0.05, 0.01], 0.0009, pairing=pairing)   # sqrt(R) = 0.03 m
+        with _ctx(api, est, gt) as ctx:
+            got = ctx.calculateMetricsWithInitialMatrix(p)
+        exp = O.eval_nn(est, gt, p)
+        assert 0 < exp.est_to_gt.n_corr < len(est)
+        _cmp_nn(got, exp)
+    # as-written pairing with more est than gt points hits the reference's out-of-range lookups
+    p = A.make_nn_params([0.2, 0.1, 0.08, 0.05, 0.01], 1.0, pairing=A.ME_PAIRING_AS_WRITTEN)
+    with _ctx(api, gt, est) as ctx:   # swap roles: n_est < n_gt -> i_gt can exceed n_est
+        got = ctx.calculateMetricsWithInitialMatrix(p)
+    exp = O.eval_nn(gt, est, p)
+    assert exp.gt_to_est.n_ub > 0
+    _cmp_nn(got, exp)
+
+
+def test_nn_far_queries_clusters_and_outliers(api, O):
+    """Queries far from every reference point (ring-expansion kernel), clustered references, duplicates."""
+    rng = np.random.RandomState(5)
+    gt = np.concatenate([rng.randn(20000, 3) * 0.3 + c for c in ([0, 0, 0], [6, 1, -2], [-3, 8, 1])])
+    gt = np.concatenate([gt, gt[:100]])                         # duplicated reference points
+    est = np.concatenate([gt[::3] + rng.randn(len(gt[::3]), 3) * 0.01,
+                          rng.rand(3000, 3) * 40 - 20,          # outliers up to ~20 m away
+                          gt[:50]])                              # exact coincidences (d = 0)
+    est = est.astype(np.float32).astype(np.float64)
+    gt = gt.astype(np.float32).astype(np.float64)
+    p = A.make_nn_params([0.5, 0.3, 0.2, 0.1, 0.05], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+    with _ctx(api, est, gt) as ctx:
+        e, g = ctx.eval_nn_accum(p)
+        got = ctx.nn_finalize(p, e, g)
+        idx_e, d2_e = ctx.get_nn(A.ME_CLOUD_EST)
+    assert e.n_far > 1000
+    exp = O.eval_nn(est, gt, p)
+    _cmp_nn(got, exp)
+    oi, od2 = O.knn1(est, gt)
+    np.testing.assert_array_equal(d2_e, od2)
+    np.testing.assert_array_equal(idx_e, oi)
+
+
+def test_nn_without_full_cd_stops_at_cutoff(api, O):
+    est, gt, cfg = synth.make_pair("C1", scale=0.3)
+    est = np.concatenate([est, est[:500] + 30.0])               # far outliers that need no exact NN
+    p = A.make_nn_params(cfg["tau"], 0.04, want_full_cd=False, pairing=A.ME_PAIRING_GEOMETRIC)
+    with _ctx(api, est, gt) as ctx:
+        got = ctx.calculateMetricsWithInitialMatrix(p)
+    exp = O.eval_nn(est, gt, p)
+    assert got.full_cd == 0.0 and exp.full_cd == 0.0
+    for d in ("est_to_gt", "gt_to_est"):
+        a, b = getattr(got, d), getattr(exp, d)
+        assert a.n_corr == b.n_corr and list(a.n_inlier) == list(b.n_inlier)
+        np.testing.assert_allclose(list(a.rmse), list(b.rmse), rtol=RTOL)
+
+
+def test_transform_then_nn(api, O):
+    est, gt, cfg = synth.make_pair("C1", scale=0.2)
+    th = 0.01
+    T = np.array([[np.cos(th), -np.sin(th), 0, 0.02], [np.sin(th), np.cos(th), 0, -0.01], [0, 0, 1, 0.005], [0, 0, 0, 1]])
+    p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+    with _ctx(api, est, gt) as ctx:
+        ctx.transform(A.ME_CLOUD_EST, T)                       # map_3d_->Transform(initial_matrix), map_eval.cpp:1206
+        got = ctx.calculateMetricsWithInitialMatrix(p)
+    exp = O.eval_nn(O.transform(est, T), gt, p)
+    _cmp_nn(got, exp)
+
+
+@pytest.mark.parametrize("min_neighbors", [10, 5])
+def test_mme_parity(api, O, min_neighbors):
+    est, gt, cfg = synth.make_pair("C2", scale=0.2)             # 200k points, r = 0.1 m
+    with _ctx(api, est, gt) as ctx:
+        got, ent = ctx.computeMME(A.ME_CLOUD_EST, cfg["nn_radius"], min_neighbors, want_entropies=True)
+    exp, oent = O.eval_mme(est, cfg["nn_radius"], min_neighbors, want_entropies=True)
+    assert got.n_valid == exp.n_valid and got.n_total == exp.n_total
+    np.testing.assert_array_equal(ent != 0, oent != 0)
+    np.testing.assert_allclose(ent, oent, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(got.mme, exp.mme, rtol=RTOL)
+    np.testing.assert_allclose(got.min_abs_entropy, exp.min_abs_entropy, rtol=RTOL)
+    np.testing.assert_allclose(got.max_abs_entropy, exp.max_abs_entropy, rtol=RTOL)
+
+
+def test_mme_sparse_and_large_radius(api, O):
+    """Radius spanning many lattice cells, surface-like data, points with too few neighbours."""
+    est = synth.outdoor_scene(120000, 77, 0.01)
+    with _ctx(api, est, est[:10]) as ctx:
+        got, ent = ctx.computeMME(A.ME_CLOUD_EST, 0.6, 10, want_entropies=True)
+    exp, oent = O.eval_mme(est, 0.6, 10, want_entropies=True)
+    assert got.n_valid == exp.n_valid
+    assert 0 < exp.n_valid < len(est)
+    np.testing.assert_array_equal(ent != 0, oent != 0)
+    np.testing.assert_allclose(ent, oent, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(got.mme, exp.mme, rtol=RTOL)
+
+
+def _sorted_rows(rows, v):
+    keys = np.rint(rows[:, 0:3] / v).astype(np.int64)
+    order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+    return rows[order]
+
+
+@pytest.mark.parametrize("hint", [True, False])
+def test_awd_scs_parity(api, O, hint):
+    est, gt, cfg = synth.make_pair("C2", scale=0.3)             # 300k points, v = 0.25 m (~195 pts / voxel)
+    v = cfg["vmd_voxel_size"]
+    kw = dict(vmd_voxel_size=v) if hint else {}
+    with _ctx(api, est, gt, **kw) as ctx:
+        if not hint:   # lattice first laid out without knowing v, then re-laid by calculateVMD
+            ctx.calculateMetricsWithInitialMatrix(A.make_nn_params(cfg["tau"], 1.0))
+        got, rows = ctx.calculateVMD(v, 100, 5, want_rows=True)
+    exp, orows = O.eval_awd(est, gt, v, 100, 5, want_rows=True)
+    for k in ("n_pairs", "n_scs", "n_voxels_est", "n_voxels_gt", "n_active", "n_old", "n_new"):
+        assert getattr(got, k) == getattr(exp, k), k
+    assert got.n_pairs > 100
+    np.testing.assert_allclose(got.awd, exp.awd, rtol=RTOL)
+    np.testing.assert_allclose(got.scs, exp.scs, rtol=RTOL)
+    a, b = _sorted_rows(rows, v), _sorted_rows(orows, v)
+    np.testing.assert_array_equal(a[:, [0, 1, 2, 3, 4, 5, 10, 11]], b[:, [0, 1, 2, 3, 4, 5, 10, 11]])
+    np.testing.assert_allclose(a[:, 6:9], b[:, 6:9], rtol=1e-12)            # mu_est
+    np.testing.assert_allclose(a[:, 18:21], b[:, 18:21], rtol=1e-12)        # mu_gt
+    np.testing.assert_allclose(a[:, 9], b[:, 9], rtol=1e-8)                 # W
+    np.testing.assert_allclose(a[:, 12:18], b[:, 12:18], rtol=1e-7, atol=1e-16)
+    np.testing.assert_allclose(a[:, 21:27], b[:, 21:27], rtol=1e-7, atol=1e-16)
+
+
+def test_awd_negative_coordinates_and_no_pairs(api, O):
+    est, gt, _ = synth.make_pair("C1", scale=0.5)
+    est = est - 7.3
+    gt = gt - 7.3
+    with _ctx(api, est, gt) as ctx:
+        got = ctx.calculateVMD(0.5, 100, 5)
+        none = ctx.calculateVMD(0.05, 100, 5)        # no voxel reaches 100 points: 0/0 -> NaN like the reference
+    exp = O.eval_awd(est, gt, 0.5, 100, 5)
+    assert (got.n_pairs, got.n_active, got.n_old, got.n_new) == (exp.n_pairs, exp.n_active, exp.n_old, exp.n_new)
+    np.testing.assert_allclose(got.awd, exp.awd, rtol=RTOL)
+    np.testing.assert_allclose(got.scs, exp.scs, rtol=RTOL)
+    assert none.n_pairs == 0 and np.isnan(none.awd) and np.isnan(none.scs)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_shard_count_invariance(api, O, world):
+    """Sharding the query range over `world` contexts and summing the accumulators reproduces world = 1."""
+    est, gt, cfg = synth.make_pair("C1", scale=0.5)
+    p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_AS_WRITTEN)
+    with _ctx(api, est, gt) as ctx:
+        ref = ctx.calculateMetricsWithInitialMatrix(p)
+        ref_m = ctx.eval_mme_accum(A.ME_CLOUD_EST, 0.1, 10)
+        tot_e, tot_g, tot_m = A.me_nn_accum(), A.me_nn_accum(), A.me_mme_accum()
+        tot_m.min_entropy, tot_m.max_entropy = np.inf, -np.inf
+        for r in range(world):
+            ctx.set_shard(r, world)
+            e, g = ctx.eval_nn_accum(p)
+            m = ctx.eval_mme_accum(A.ME_CLOUD_EST, 0.1, 10)
+            for tot, part in ((tot_e, e), (tot_g, g)):
+                for name, ctype in A.me_nn_accum._fields_:
+                    v = getattr(part, name)
+                    if hasattr(v, "__len__"):
+                        for i in range(len(v)):
+                            getattr(tot, name)[i] += v[i]
+                    else:
+                        setattr(tot, name, getattr(tot, name) + v)
+            tot_m.n_query += m.n_query; tot_m.n_valid += m.n_valid; tot_m.sum_entropy += m.sum_entropy
+            tot_m.min_entropy = min(tot_m.min_entropy, m.min_entropy)
+            tot_m.max_entropy = max(tot_m.max_entropy, m.max_entropy)
+        got = ctx.nn_finalize(p, tot_e, tot_g)
+    assert tot_e.n_query == len(est) and tot_g.n_query == len(gt)
+    _cmp_nn(got, ref)
+    assert tot_m.n_valid == ref_m.n_valid
+    np.testing.assert_allclose(tot_m.sum_entropy, ref_m.sum_entropy, rtol=1e-12)
+    assert (tot_m.min_entropy, tot_m.max_entropy) == (ref_m.min_entropy, ref_m.max_entropy)
+
+
+def test_device_resident_cloud_and_errors(api):
+    import torch
+    est, gt, cfg = synth.make_pair("C1", scale=0.1)
+    p = A.make_nn_params(cfg["tau"], 1.0)
+    with _ctx(api, est, gt) as ctx:
+        ref = ctx.calculateMetricsWithInitialMatrix(p)
+    te, tg = torch.from_numpy(est).cuda(), torch.from_numpy(gt).cuda()
+    with api.MapEvalB200(stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        with pytest.raises(api.MapEvalError):
+            ctx.calculateMetricsWithInitialMatrix(p)             # clouds not set -> ME_ERR_EMPTY
+        ctx.set_cloud_device(A.ME_CLOUD_EST, te.data_ptr(), len(est), keepalive=te)
+        ctx.set_cloud_device(A.ME_CLOUD_GT, tg.data_ptr(), len(gt), keepalive=tg)
+        got = ctx.calculateMetricsWithInitialMatrix(p)
+        assert list(got.est_to_gt.n_inlier) == list(ref.est_to_gt.n_inlier)
+        assert got.full_cd == pytest.approx(ref.full_cd, rel=1e-12)
+        bad = est.copy(); bad[3, 1] = np.nan
+        ctx.set_cloud(A.ME_CLOUD_EST, bad)
+        with pytest.raises(api.MapEvalError):
+            ctx.calculateMetricsWithInitialMatrix(p)             # non-finite coordinates are rejected
+        assert ctx.launch_count() > 0
