@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — Mpts/s of one full MapEval metric pass (AC + CD + full CD + MME + voxel Gaussians + AWD + SCS).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3] [--impl reference]
+
+A step = one pass of the hot path over one synthetic cloud pair: both lattices are laid out from
+the fp64 clouds, NN est->gt and gt->est with the five-threshold accumulators and the full-Chamfer sums, MME of the
+estimated map (and of the GT map when the config says so), per-voxel Gaussians, AWD and SCS.
+  value : est points / step time with both clouds already resident in HBM (device-resident arm)
+  e2e   : the same pass through the C-ABI with HOST (pinned) buffers: H2D of both clouds and D2H of the result
+          structs are inside the timed region
+N > 1 (torchrun, one rank per GPU): the query ranges of the NN and MME sweeps are sharded by rank, both lattices are
+replicated, and the sum-reducible accumulators are all-reduced over NCCL once per step (strong scaling: the cloud
+pair is fixed).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cloud_map_evaluation_b200 import _abi as A  # noqa: E402
+from cloud_map_evaluation_b200 import synth  # noqa: E402
+
+METRIC = "Mpts/s full AC+CD+AWD+MME pass"
+UNIT = "Mpts/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _profile_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if present."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sel = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for (_, r) in self.rows]
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in sel:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except Exception:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _cpu_pass(est, gt, cfg, threads):
+    """One full pass with the oracle (the CPU restatement of the reference)."""
+    from oracle import oracle as O
+    p = A.make_nn_params(cfg["tau"], 1.0)
+    t0 = time.perf_counter()
+    O.eval_nn(est, gt, p, threads=threads)
+    if cfg["mme"]:
+        O.eval_mme(est, cfg["nn_radius"], 10, threads=threads)
+        if cfg["gt_mme"]:
+            O.eval_mme(gt, cfg["nn_radius"], 5, threads=threads)
+    if cfg["awd"]:
+        O.eval_awd(est, gt, cfg["vmd_voxel_size"], 100, 5)
+    return time.perf_counter() - t0
+
+
+def _cpu_sample(name, target_pts=1_000_000):
+    base = synth.CONFIGS[name]
+    scale = min(1.0, target_pts / base["n_est"])
+    est, gt, cfg = synth.make_pair(name, scale=scale)
+    return est, gt, cfg, scale
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: Open3D/Eigen/TBB are absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.num_threads()
+    est, gt, cfg, scale = _cpu_sample(args.config)
+    for _ in range(min(args.warmup, 1)):
+        _cpu_pass(est, gt, cfg, threads)
+    times = [_cpu_pass(est, gt, cfg, threads) for _ in range(args.steps)]
+    dt = float(np.mean(times))
+    v = len(est) / dt / 1e6
+    sample = f"{args.config} at scale {scale:g} ({len(est)} est vs {len(gt)} gt points, same density), full pass, all-cores mode"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def _allreduce_accs(dist, torch, dev, nn_e, nn_g, mme_list):
+    """One SUM all-reduce over the int64 block, one over the fp64 block, one MIN/MAX pair for the entropy extrema."""
+    ints, flts, mins, maxs = [], [], [], []
+    for a in (nn_e, nn_g):
+        ints += [a.n_query, a.n_corr] + list(a.n_inlier) + [a.n_ub, a.n_far]
+        flts += list(a.sum_d) + list(a.sum_d2) + [a.sum_d_all, a.sum_d2_all, a.sum_nn_dist]
+    for m in mme_list:
+        ints += [m.n_query, m.n_valid]
+        flts += [m.sum_entropy]
+        mins.append(m.min_entropy); maxs.append(m.max_entropy)
+    ti = torch.tensor(ints, dtype=torch.int64, device=dev)
+    tf = torch.tensor(flts, dtype=torch.float64, device=dev)
+    dist.all_reduce(ti); dist.all_reduce(tf)
+    if mins:
+        tmin = torch.tensor(mins, dtype=torch.float64, device=dev)
+        tmax = torch.tensor(maxs, dtype=torch.float64, device=dev)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ti, tf = ti.cpu().tolist(), tf.cpu().tolist()
+    ii = fi = 0
+    for a in (nn_e, nn_g):
+        a.n_query, a.n_corr = ti[ii], ti[ii + 1]
+        for k in range(5):
+            a.n_inlier[k] = ti[ii + 2 + k]
+        a.n_ub, a.n_far = ti[ii + 7], ti[ii + 8]
+        ii += 9
+        for k in range(5):
+            a.sum_d[k] = tf[fi + k]; a.sum_d2[k] = tf[fi + 5 + k]
+        a.sum_d_all, a.sum_d2_all, a.sum_nn_dist = tf[fi + 10], tf[fi + 11], tf[fi + 12]
+        fi += 13
+    for j, m in enumerate(mme_list):
+        m.n_query, m.n_valid = ti[ii], ti[ii + 1]; ii += 2
+        m.sum_entropy = tf[fi]; fi += 1
+        m.min_entropy, m.max_entropy = float(tmin[j]), float(tmax[j])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C3", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; not a bench line)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cloud_map_evaluation_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmapeval_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    est, gt, cfg = synth.make_pair(args.config, scale=args.scale)
+    n_est, n_gt = len(est), len(gt)
+    p = A.make_nn_params(cfg["tau"], 1.0)        # path A as written + full CD
+
+    # pinned host copies (e2e arm) and device-resident copies (value arm)
+    h_est = torch.from_numpy(est).pin_memory()
+    h_gt = torch.from_numpy(gt).pin_memory()
+    d_est = h_est.to(dev)
+    d_gt = h_gt.to(dev)
+    stream = torch.cuda.current_stream()
+    ctx = api.MapEvalB200(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream,
+                          vmd_voxel_size=cfg["vmd_voxel_size"] if cfg["awd"] else 0.0)
+
+    results = {}
+
+    def one_pass(host_buffers):
+        if host_buffers:
+            ctx.set_cloud_ptr(A.ME_CLOUD_EST, h_est.data_ptr(), n_est, keepalive=h_est)
+            ctx.set_cloud_ptr(A.ME_CLOUD_GT, h_gt.data_ptr(), n_gt, keepalive=h_gt)
+        else:
+            ctx.set_cloud_device(A.ME_CLOUD_EST, d_est.data_ptr(), n_est, keepalive=d_est)
+            ctx.set_cloud_device(A.ME_CLOUD_GT, d_gt.data_ptr(), n_gt, keepalive=d_gt)
+        nn_e, nn_g = ctx.eval_nn_accum(p)
+        mmes = []
+        if cfg["mme"]:
+            mmes.append(ctx.eval_mme_accum(A.ME_CLOUD_EST, cfg["nn_radius"], 10))
+            if cfg["gt_mme"]:
+                mmes.append(ctx.eval_mme_accum(A.ME_CLOUD_GT, cfg["nn_radius"], 5))
+        awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5) if cfg["awd"] else None
+        if world > 1:
+            _allreduce_accs(dist, torch, dev, nn_e, nn_g, mmes)
+        results["nn"] = ctx.nn_finalize(p, nn_e, nn_g)
+        results["mme"] = [ctx.mme_finalize(m, w) for m, w in zip(mmes, (A.ME_CLOUD_EST, A.ME_CLOUD_GT))]
+        results["awd"] = awd
+        results["n_far"] = (nn_e.n_far, nn_g.n_far)
+
+    def timed(host_buffers, steps, stage_acc=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        t0 = time.time()
+        ev0.record(stream)
+        for _ in range(steps):
+            one_pass(host_buffers)
+            if stage_acc is not None:
+                for k, v in ctx.stage_times_ms().items():
+                    stage_acc[k] = stage_acc.get(k, 0.0) + v
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t1 = time.time()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, ctx.launch_count() - l0, t0, t1
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        one_pass(False)
+    stage_ms = {}
+    ms_dev, launches, t0, t1 = timed(False, args.steps, stage_ms)
+    for _ in range(min(args.warmup, 2)):
+        one_pass(True)
+    ms_e2e, _, _, t1b = timed(True, args.steps)
+    clocks = sampler.stop(t0, t1b) if sampler else None
+
+    if rank == 0:
+        stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+        value = n_est / (ms_dev * 1e-3) / 1e6
+        e2e = n_est / (ms_e2e * 1e-3) / 1e6
+        peak, peak_src = _peaks()
+        # dominant kernel: the MME radius sweep of the estimated map (stage "mme_est" = mme_kernel + a 1-thread init).
+        # algorithmic bytes per launch: 12 B query + 12 B reference + 8 B entropy out per point of this
+        # rank's query range
+        nq = n_est * (rank + 1) // world - n_est * rank // world
+        dom = "mme_est" if cfg["mme"] else "nn_est_to_gt"
+        alg_bytes = (32.0 * nq) if cfg["mme"] else (12.0 * (nq + n_gt))
+        dom_ms = stage_ms.get(dom, 0.0)
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+        traffic = _profile_traffic()
+        roofline = {"bound": "hbm", "kernel": "mme_kernel" if cfg["mme"] else "nn_sweep_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
+                    "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                    "note": "issue/FP64-bound neighbour sweep; the HBM fraction is small by construction (SURVEY §8d)"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            threads = O.num_threads()
+            s_est, s_gt, s_cfg, s_scale = _cpu_sample(args.config)
+            dt = _cpu_pass(s_est, s_gt, s_cfg, threads)
+            cpu = {"value": len(s_est) / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{args.config} at scale {s_scale:g} ({len(s_est)} est vs {len(s_gt)} gt points, same "
+                             f"density), one full pass in {dt:.1f} s, all-cores mode"}
+        nn = results["nn"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "n_est": n_est,
+                       "n_gt": n_gt, "tau": cfg["tau"], "icp_max_distance": 1.0, "nn_radius": cfg["nn_radius"],
+                       "vmd_voxel_size": cfg["vmd_voxel_size"], "mme_gt": bool(cfg["gt_mme"]),
+                       "parallelism": f"query-range shard x{world}, lattices replicated",
+                       "l2": "inputs (2 x 240 MB fp64 + 2 x 320 MB sorted) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 24 * (n_est + n_gt),
+                    "d2h_bytes_per_step": 2 * C.sizeof(A.me_nn_accum) + C.sizeof(A.me_mme_accum) * len(results["mme"])
+                    + C.sizeof(A.me_awd_result)},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "stage_ms": stage_ms,
+            "check": {"AC_rmse": list(nn.est_to_gt.rmse), "n_inlier": list(nn.est_to_gt.n_inlier),
+                      "full_cd": nn.full_cd, "mme": [m.mme for m in results["mme"]],
+                      "awd": results["awd"].awd if results["awd"] else None,
+                      "scs": results["awd"].scs if results["awd"] else None, "n_far": list(results["n_far"])},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
