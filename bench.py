@@ -231,12 +231,14 @@ def main():
         else:
             ctx.set_cloud_device(A.ME_CLOUD_EST, d_est.data_ptr(), n_est, keepalive=d_est)
             ctx.set_cloud_device(A.ME_CLOUD_GT, d_gt.data_ptr(), n_gt, keepalive=d_gt)
-        nn_e, nn_g = ctx.eval_nn_accum(p)
+        # MapEval::process() order (map_eval.cpp:56,76,85): MME, then the NN metrics, then VMD.  With host buffers
+        # the GT upload (copy stream) overlaps the est lattice build + MME, which need the est cloud only.
         mmes = []
         if cfg["mme"]:
             mmes.append(ctx.eval_mme_accum(A.ME_CLOUD_EST, cfg["nn_radius"], 10))
             if cfg["gt_mme"]:
                 mmes.append(ctx.eval_mme_accum(A.ME_CLOUD_GT, cfg["nn_radius"], 5))
+        nn_e, nn_g = ctx.eval_nn_accum(p)
         awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5) if cfg["awd"] else None
         if world > 1:
             _allreduce_accs(dist, torch, dev, nn_e, nn_g, mmes)

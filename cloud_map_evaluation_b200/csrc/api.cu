@@ -57,6 +57,8 @@ static void free_cloud(Cloud &c) {
   if (c.d_nn_idx) cudaFree(c.d_nn_idx);
   if (c.d_nn_d2) cudaFree(c.d_nn_d2);
   if (c.d_entropy) cudaFree(c.d_entropy);
+  if (c.d_tiles) cudaFree(c.d_tiles);
+  if (c.upload_done) cudaEventDestroy(c.upload_done);
   c = Cloud();
 }
 
@@ -110,6 +112,9 @@ int me_create(const me_options *opt, me_ctx **out) {
     ctx->own_stream = true;
   }
   bool ok = cudaMalloc(&ctx->d_scratch, kScratchBytes) == cudaSuccess && cudaMallocHost(&ctx->h_pinned, kScratchBytes) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->compute_mark, cudaEventDisableTiming) == cudaSuccess;
+  for (int w = 0; ok && w < 2; ++w) ok = cudaEventCreateWithFlags(&ctx->cloud[w].upload_done, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2 * ME_N_STAGE_TIMES; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
   for (int i = 0; i < ME_N_STAGE_TIMES; ++i) ctx->ev_used[i] = false;
   if (!ok) { me_destroy(ctx); return fail(nullptr, ME_ERR_NOMEM, "context allocation failed"); }
@@ -122,6 +127,8 @@ void me_destroy(me_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->compute_mark) cudaEventDestroy(ctx->compute_mark);
   free_cloud(ctx->cloud[0]);
   free_cloud(ctx->cloud[1]);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -157,6 +164,7 @@ int me_set_shard(me_ctx *ctx, int32_t rank, int32_t world) {
 
 int me_synchronize(me_ctx *ctx) {
   ME_ENTER(ctx);
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ME_OK;
 }
@@ -172,7 +180,15 @@ int me_set_cloud(me_ctx *ctx, int which, const double *xyz_host, int64_t n) {
   c.owned = true;
   c.n = n;
   invalidate(c);
-  if (n > 0) ME_CUDA(ctx, cudaMemcpyAsync(c.d_xyz, xyz_host, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (n > 0) {
+    // the copy runs on its own stream: it may overlap kernels that work on the other cloud, but must not overtake
+    // kernels already queued that still read this buffer
+    ME_CUDA(ctx, cudaEventRecord(ctx->compute_mark, ctx->stream));
+    ME_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_mark, 0));
+    ME_CUDA(ctx, cudaMemcpyAsync(c.d_xyz, xyz_host, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+    ME_CUDA(ctx, cudaEventRecord(c.upload_done, ctx->copy_stream));
+    c.upload_pending = true;
+  }
   return ME_OK;
 }
 
@@ -186,6 +202,7 @@ int me_set_cloud_device(me_ctx *ctx, int which, const double *xyz_device, int64_
   c.d_xyz = const_cast<double *>(xyz_device);
   c.cap_xyz = 0;
   c.owned = false;
+  c.upload_pending = false;
   c.n = n;
   invalidate(c);
   return ME_OK;

@@ -9,12 +9,16 @@
 namespace me {
 
 // One point of a cell-sorted cloud: absolute fp64 coordinates (the reference's storage type,
-// std::vector<Eigen::Vector3d>) + the index the point had in the caller's array.  32 B, so a point is two
-// aligned 16-byte loads.
+// std::vector<Eigen::Vector3d>) + a tag: low 32 bits = index the point had in the caller's array, high 32 bits =
+// lattice cell of the point.  32 B, so a point is two aligned 16-byte loads (and a valid TMA bulk-copy unit).
 struct __align__(32) P4 {
   double x, y, z;
   long long idx;
 };
+__host__ __device__ __forceinline__ int orig_of(long long tag) { return (int)(tag & 0xffffffffll); }
+__host__ __device__ __forceinline__ unsigned int cell_of(long long tag) { return (unsigned int)((unsigned long long)tag >> 32); }
+
+static constexpr int kTileEdge = 4;   // query tiles are kTileEdge^3 cells
 
 // Dense lattice of a cloud.  Cells are cubes of edge h = v / m whose boundaries coincide with the voxel
 // boundaries floor(x / v) of the reference (voxel_calculator.cpp:241-245): every cell belongs to exactly one
@@ -27,6 +31,7 @@ struct Lattice {
   int k_lo[3];       // lowest voxel index per axis (floor(min / v))
   int nvox[3];       // voxels per axis
   int dims[3];       // cells per axis = nvox * m
+  int nb[3];         // tiles (kTileEdge^3 cells) per axis
   long long ncells;
   long long nvoxels;
 };
@@ -46,6 +51,11 @@ struct Cloud {
   long long cap_cells = 0;
   uint32_t *d_cell_id = nullptr;    // scratch: cell of each point (caller order)
   long long cap_cell_id = 0;
+  uint32_t *d_tiles = nullptr;      // non-empty query tiles (tile id = (bz*nb[1]+by)*nb[0]+bx)
+  long long cap_tiles = 0;
+  long long n_tiles = 0;
+  cudaEvent_t upload_done = nullptr;  // recorded on the copy stream after me_set_cloud's H2D
+  bool upload_pending = false;
   // per-query results, SORTED order of this cloud (unsorted on demand)
   int32_t *d_nn_idx = nullptr;      // nearest neighbour in the other cloud (caller index there)
   double *d_nn_d2 = nullptr;
@@ -66,6 +76,11 @@ struct me_ctx {
   double nn_cell_size = 0.0;
   long long max_grid_cells = 1ll << 28;
   double voxel_hint = 0.0;          // lattice alignment requested by the voxel stage
+  // lattice spec shared by both clouds, so that their cells coincide (same v, m; integer index offsets)
+  double spec_v = 0.0;
+  int spec_m = 0;
+  cudaStream_t copy_stream = nullptr;   // H2D uploads run here and overlap kernels that do not need them yet
+  cudaEvent_t compute_mark = nullptr;
   me::Cloud cloud[2];
   // small device scratch for reductions / accumulators
   void *d_scratch = nullptr;
@@ -121,8 +136,10 @@ struct StageTimer {
 };
 
 // stage entry points (implemented in grid.cu / nn.cu / mme.cu / voxel.cu)
+int wait_upload(me_ctx *ctx, int which);
 int compute_bbox(me_ctx *ctx, int which);
 int build_grid(me_ctx *ctx, int which);
+int build_both(me_ctx *ctx);
 int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e);
 int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2);
 int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out);

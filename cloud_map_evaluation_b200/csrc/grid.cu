@@ -55,10 +55,21 @@ __global__ void __launch_bounds__(kThreads) bbox_kernel(const double *__restrict
   }
 }
 
+// kernels on the compute stream must not read a cloud before its H2D copy (on the copy stream) has landed
+int wait_upload(me_ctx *ctx, int which) {
+  Cloud &c = ctx->cloud[which];
+  if (c.upload_pending) {
+    ME_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c.upload_done, 0));
+    c.upload_pending = false;
+  }
+  return ME_OK;
+}
+
 int compute_bbox(me_ctx *ctx, int which) {
   Cloud &c = ctx->cloud[which];
   if (c.bbox_valid) return ME_OK;
   if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
+  ME_TRY(wait_upload(ctx, which));
   unsigned long long *s = (unsigned long long *)ctx->d_scratch;
   bbox_init_kernel<<<1, 32, 0, ctx->stream>>>(s);
   ME_LAUNCH_CHECK(ctx);
@@ -202,7 +213,31 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const double *__restr
     double x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
     double2 *o = reinterpret_cast<double2 *>(sorted + slot);
     o[0] = make_double2(x, y);
-    o[1] = make_double2(z, __longlong_as_double(i));
+    o[1] = make_double2(z, __longlong_as_double((long long)(((unsigned long long)c << 32) | (unsigned long long)i)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// query tiles: every kTileEdge^3 block of cells that holds at least one point (from the histogram, before the scan)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) tile_list_kernel(const uint32_t *__restrict__ count, Lattice L,
+                                                             uint32_t *__restrict__ tiles,
+                                                             unsigned long long *__restrict__ n_tiles) {
+  const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nt; t += (long long)gridDim.x * blockDim.x) {
+    const int bx = (int)(t % L.nb[0]), by = (int)((t / L.nb[0]) % L.nb[1]), bz = (int)(t / ((long long)L.nb[0] * L.nb[1]));
+    uint32_t tot = 0;
+    for (int dz = 0; dz < kTileEdge; ++dz) {
+      const int z = bz * kTileEdge + dz;
+      if (z >= L.dims[2]) break;
+      for (int dy = 0; dy < kTileEdge; ++dy) {
+        const int y = by * kTileEdge + dy;
+        if (y >= L.dims[1]) break;
+        const long long row = ((long long)z * L.dims[1] + y) * L.dims[0] + (long long)bx * kTileEdge;
+        for (int dx = 0; dx < kTileEdge && bx * kTileEdge + dx < L.dims[0]; ++dx) tot += __ldg(count + row + dx);
+      }
+    }
+    if (tot) tiles[atomicAdd(n_tiles, 1ull)] = (uint32_t)t;
   }
 }
 
@@ -221,6 +256,7 @@ static bool make_lattice(const Cloud &c, double v, int m, long long budget, Latt
     if (nvx * m > 2.0e9) return false;
     L.nvox[a] = (int)nvx;
     L.dims[a] = L.nvox[a] * m;
+    L.nb[a] = (L.dims[a] + kTileEdge - 1) / kTileEdge;
     if ((double)nc * L.dims[a] > 4.0e9) return false;
     nc *= L.dims[a];
     nv *= L.nvox[a];
@@ -255,58 +291,103 @@ static int occupancy(me_ctx *ctx, Cloud &c, const Lattice &L, long long *occupie
   return ME_OK;
 }
 
-int build_grid(me_ctx *ctx, int which) {
-  Cloud &c = ctx->cloud[which];
-  if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
-  if (c.n >= 0x7fffffffll) return fail(ctx, ME_ERR_RANGE, "more than 2^31-1 points per cloud (the reference indexes with int)");
-  if (c.grid_valid) return ME_OK;
-  StageTimer timer(ctx, which == ME_CLOUD_EST ? 0 : 1);
-  ME_TRY(compute_bbox(ctx, which));
-
-  const long long budget = ctx->max_grid_cells;
+// h the cloud would like on its own: ~2 points per cell for a volume-filling cloud
+static double density_edge(const Cloud &c) {
   double ext[3], vol = 1.0, ext_max = 0.0;
   for (int a = 0; a < 3; ++a) { ext[a] = c.bbox_max[a] - c.bbox_min[a]; ext_max = std::max(ext_max, ext[a]); }
   if (ext_max <= 0.0) ext_max = 1.0;
   for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * ext_max);
+  return std::cbrt(2.0 * vol / (double)c.n);
+}
 
-  // target edge: ~2 points per cell for a volume-filling cloud; refined below from the measured occupancy
-  double h_target = ctx->nn_cell_size > 0 ? ctx->nn_cell_size : std::cbrt(2.0 * vol / (double)c.n);
-  const double v_req = ctx->voxel_hint;
-  Lattice L;
-  bool have = false;
-  for (int iter = 0; iter < 4; ++iter) {
-    // pick (v, m): aligned to the voxel size when one is known, free otherwise
-    bool ok = false;
-    Lattice cand;
-    if (v_req > 0) {
-      int m = (int)std::max(1.0, std::floor(v_req / h_target + 0.5));
-      m = std::min(m, 1 << 20);
-      for (; m >= 1; --m) {
-        if (make_lattice(c, v_req, m, budget, &cand)) { ok = true; break; }
-        if (m > 64) m = (int)(m * 0.8);   // far over budget: shrink geometrically
+// (v, m) for a target cell edge, fitting `c` (and `other`, if its bbox is known) into the budget
+static bool pick_spec(const Cloud &c, const Cloud *other, double v_req, double h_target, long long budget, double *v,
+                      int *m, Lattice *out) {
+  Lattice tmp;
+  if (v_req > 0) {
+    int mm = (int)std::max(1.0, std::floor(v_req / h_target + 0.5));
+    mm = std::min(mm, 1 << 20);
+    for (; mm >= 1; --mm) {
+      if (make_lattice(c, v_req, mm, budget, out) && (!other || make_lattice(*other, v_req, mm, budget, &tmp))) {
+        *v = v_req; *m = mm;
+        return true;
       }
-      if (!ok)
-        return fail(ctx, ME_ERR_RANGE, "voxel size too small for the dense lattice budget (raise max_grid_cells)");
-    } else {
-      double h = h_target;
-      for (int t = 0; t < 64 && !ok; ++t) { ok = make_lattice(c, h, 1, budget, &cand); if (!ok) h *= 1.26; }
-      if (!ok) return fail(ctx, ME_ERR_RANGE, "cannot fit the cloud into the dense lattice budget");
+      if (mm > 64) mm = (int)(mm * 0.8);   // far over budget: shrink geometrically
     }
-    if (have && cand.ncells == L.ncells && cand.m == L.m && cand.v == L.v) break;  // refinement changed nothing
-    L = cand; have = true;
-    ME_TRY(histogram(ctx, c, L));
-    if (ctx->nn_cell_size > 0) break;   // caller fixed the cell size
-    long long occupied = 0, max_count = 0;
-    ME_TRY(occupancy(ctx, c, L, &occupied, &max_count));
-    double mean_occ = (double)c.n / (double)std::max<long long>(1, occupied);
-    if (mean_occ <= 4.0 || iter == 3) break;
-    // surface-like data: occupancy of occupied cells scales ~h^2; aim at ~2 points per occupied cell
-    double shrink = std::sqrt(2.0 / mean_occ);
-    double h_new = std::max(L.h * shrink, L.h * 0.25);
-    if (h_new >= 0.9 * L.h) break;
-    h_target = h_new;
+    return false;
   }
+  double h = h_target;
+  for (int t = 0; t < 96; ++t, h *= 1.26)
+    if (make_lattice(c, h, 1, budget, out) && (!other || make_lattice(*other, h, 1, budget, &tmp))) {
+      *v = h; *m = 1;
+      return true;
+    }
+  return false;
+}
+
+int build_grid(me_ctx *ctx, int which) {
+  Cloud &c = ctx->cloud[which];
+  Cloud &o = ctx->cloud[1 - which];
+  if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
+  if (c.n >= 0x7fffffffll) return fail(ctx, ME_ERR_RANGE, "more than 2^31-1 points per cloud (the reference indexes with int)");
+  if (c.grid_valid) return ME_OK;
+  ME_TRY(wait_upload(ctx, which));
+  StageTimer timer(ctx, which == ME_CLOUD_EST ? 0 : 1);
+  ME_TRY(compute_bbox(ctx, which));
+  const long long budget = ctx->max_grid_cells;
+  const double v_req = ctx->voxel_hint;
+
+  // Both clouds share one lattice spec (v, m) so that their cells coincide.  The spec is re-planned whenever no
+  // valid grid depends on it (i.e. at the first build of a pass); a later build re-uses it.
+  bool planned_here = false;
+  Lattice L;
+  if (o.grid_valid && ctx->spec_m > 0 && (v_req <= 0 || ctx->spec_v == v_req) &&
+      make_lattice(c, ctx->spec_v, ctx->spec_m, budget, &L)) {
+    ME_TRY(histogram(ctx, c, L));
+  } else {
+    if (o.grid_valid) {   // the other grid's spec cannot host this cloud: both are laid out again
+      o.grid_valid = false; o.nn_valid = false; o.entropy_valid = false;
+    }
+    planned_here = true;
+    const Cloud *other = (o.n > 0 && o.bbox_valid) ? &o : nullptr;
+    double h_target = ctx->nn_cell_size > 0 ? ctx->nn_cell_size : density_edge(c);
+    bool have = false;
+    for (int iter = 0; iter < 4; ++iter) {
+      Lattice cand;
+      double v; int m;
+      if (!pick_spec(c, other, v_req, h_target, budget, &v, &m, &cand))
+        return fail(ctx, ME_ERR_RANGE, v_req > 0 ? "voxel size too small for the dense lattice budget (raise max_grid_cells)"
+                                                 : "cannot fit the cloud into the dense lattice budget");
+      if (have && cand.ncells == L.ncells && cand.m == L.m && cand.v == L.v) break;   // refinement changed nothing
+      L = cand; have = true;
+      ctx->spec_v = v; ctx->spec_m = m;
+      ME_TRY(histogram(ctx, c, L));
+      if (ctx->nn_cell_size > 0) break;   // caller fixed the cell size
+      long long occupied = 0, max_count = 0;
+      ME_TRY(occupancy(ctx, c, L, &occupied, &max_count));
+      const double mean_occ = (double)c.n / (double)std::max<long long>(1, occupied);
+      if (mean_occ <= 4.0 || iter == 3) break;
+      // surface-like data: occupancy of occupied cells scales ~h^2; aim at ~2 points per occupied cell
+      const double h_new = std::max(L.h * std::sqrt(2.0 / mean_occ), L.h * 0.25);
+      if (h_new >= 0.9 * L.h) break;
+      h_target = h_new;
+    }
+  }
+  (void)planned_here;
   c.lat = L;
+
+  // non-empty query tiles, from the histogram
+  const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
+  ME_TRY(ensure(ctx, (void **)&c.d_tiles, &c.cap_tiles, std::min<long long>(nt, c.n), sizeof(uint32_t)));
+  unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
+  ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), ctx->stream));
+  {
+    int blocks = (int)std::min<long long>((nt + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+    tile_list_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L, c.d_tiles, d_nt);
+    ME_LAUNCH_CHECK(ctx);
+  }
+  unsigned long long *h_nt = (unsigned long long *)ctx->h_pinned + 8;
+  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 
   // exclusive scan of the histogram, in place
   long long ntiles = (L.ncells + kScanTile - 1) / kScanTile;
@@ -323,6 +404,8 @@ int build_grid(me_ctx *ctx, int which) {
   int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
   scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
   ME_LAUNCH_CHECK(ctx);
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  c.n_tiles = (long long)*h_nt;
   c.grid_valid = true;
   c.nn_valid = false;
   c.entropy_valid = false;
@@ -350,6 +433,7 @@ int transform_cloud(me_ctx *ctx, int which, const double T[16]) {
   Cloud &c = ctx->cloud[which];
   if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
   if (!c.owned) return fail(ctx, ME_ERR_INVALID, "me_transform needs a library-owned cloud (use me_set_cloud)");
+  ME_TRY(wait_upload(ctx, which));
   Mat16 M;
   std::memcpy(M.t, T, sizeof(M.t));
   int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);

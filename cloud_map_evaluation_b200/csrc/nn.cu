@@ -13,6 +13,7 @@
 // distance does not beat the distance to the faces of its searched block is finished by a warp-per-query
 // ring-expansion kernel (rare: ~0.1 % of queries on volume-filling clouds).
 #include "common.cuh"
+#include "tile.cuh"
 #include <algorithm>
 #include <cstring>
 
@@ -83,15 +84,16 @@ __device__ void flush_acc(LocalAcc &a, AccBlock *g) {
     for (int k = 0; k < 7; ++k) sh_i[warp][k] = (unsigned long long)iv[k];
   }
   __syncthreads();
+  const int nwarps = blockDim.x >> 5;
   if (threadIdx.x < 13) {
     double s = 0;
-    for (int w = 0; w < kThreads / 32; ++w) s += sh_d[w][threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) s += sh_d[w][threadIdx.x];
     double *dst = &g->sum_d[0];
     if (s != 0.0) atomicAdd(dst + threadIdx.x, s);
   } else if (threadIdx.x >= 32 && threadIdx.x < 39) {
     int k = threadIdx.x - 32;
     unsigned long long s = 0;
-    for (int w = 0; w < kThreads / 32; ++w) s += sh_i[w][k];
+    for (int w = 0; w < nwarps; ++w) s += sh_i[w][k];
     unsigned long long *dst = &g->n_corr;   // n_corr, n_inl[5], n_ub are contiguous
     if (s) atomicAdd(dst + k, s);
   }
@@ -106,96 +108,249 @@ __device__ __forceinline__ double face_dist_cells(double u, long long ic, int r,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// main sweep
+// shared pieces of the sweep
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-nn_sweep_kernel(const P4 *__restrict__ Q, long long q_begin, long long q_end, const P4 *__restrict__ R,
-                const uint32_t *__restrict__ cell_off, Lattice L, NNConst C, int32_t *__restrict__ nn_idx,
-                double *__restrict__ nn_d2, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count,
-                AccBlock *__restrict__ acc) {
+struct Best {
+  double d2; int idx; double dx, dy, dz;
+  __device__ __forceinline__ void init() { d2 = INFINITY; idx = 0x7fffffff; dx = dy = dz = 0; }
+  // exact fp64 evaluation in the reference's operation order; ties go to the smaller caller index
+  __device__ __forceinline__ bool offer(const P4 &q, double px, double py, double pz, int pidx) {
+    const double ddx = __dsub_rn(q.x, px), ddy = __dsub_rn(q.y, py), ddz = __dsub_rn(q.z, pz);
+    const double v = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+    if (v < d2 || (v == d2 && pidx < idx)) { d2 = v; idx = pidx; dx = ddx; dy = ddy; dz = ddz; return true; }
+    return false;
+  }
+};
+
+// 3x3x3 block around reference cell (ix,iy,iz), straight from global memory (fallback path)
+__device__ __forceinline__ void search_block_global(const P4 &q, long long ix, long long iy, long long iz,
+                                                    const P4 *__restrict__ R, const uint32_t *__restrict__ cell_off,
+                                                    const Lattice &L, Best &b) {
+  const int x0 = (int)max(ix - 1, 0ll), x1 = (int)min(ix + 1, (long long)L.dims[0] - 1);
+  if (x0 > x1) return;
+  for (int dz = -1; dz <= 1; ++dz) {
+    const long long z = iz + dz;
+    if (z < 0 || z >= L.dims[2]) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const long long y = iy + dy;
+      if (y < 0 || y >= L.dims[1]) continue;
+      const long long row = (z * L.dims[1] + y) * (long long)L.dims[0];
+      const uint32_t s = __ldg(cell_off + row + x0), e = __ldg(cell_off + row + x1 + 1);
+      for (uint32_t j = s; j < e; ++j) {
+        const P4 p = load_p4(R + j);
+        b.offer(q, p.x, p.y, p.z, orig_of(p.idx));
+      }
+    }
+  }
+}
+
+// after the 3x3x3 block: is the best provably the global nearest neighbour?  If so fold it into the accumulators,
+// otherwise hand the query to the ring-expansion kernel.
+__device__ __forceinline__ void finish_query(const P4 &q, uint32_t i, long long ix, long long iy, long long iz,
+                                             const Lattice &L, const NNConst &C, const Best &b,
+                                             int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
+                                             uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count,
+                                             LocalAcc &a) {
+  const double ux = cell_coord_cont(q.x, L, 0), uy = cell_coord_cont(q.y, L, 1), uz = cell_coord_cont(q.z, L, 2);
+  const double g = fmin(fmin(face_dist_cells(ux, ix, 1, L.dims[0]), face_dist_cells(uy, iy, 1, L.dims[1])),
+                        face_dist_cells(uz, iz, 1, L.dims[2])) * L.h;
+  const double slack = 1e-9 * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
+  const double ge = g - slack;
+  const double ge2 = ge > 0 ? ge * ge : 0.0;
+  bool resolved = b.d2 < ge2;
+  bool beyond = false;
+  if (!resolved && ge2 > C.max_d2) { resolved = true; beyond = b.d2 > C.max_d2; }   // nothing farther matters
+  if (!resolved) {
+    nn_idx[i] = b.d2 < INFINITY ? b.idx : -1;
+    nn_d2[i] = b.d2;
+    far_list[atomicAdd(far_count, 1u)] = i;
+    return;
+  }
+  if (beyond || !(b.d2 < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; return; }
+  nn_idx[i] = b.idx;
+  nn_d2[i] = b.d2;
+  if (C.want_full_cd) a.sum_nn += __dsqrt_rn(b.d2);        // map_eval.cpp:1416
+  if (C.accumulate && keep_pair(b.d2, C)) accum_pair(b.dx, b.dy, b.dz, C, a);
+}
+
+// clamp a (possibly far outside) lattice coordinate to one cell beyond the lattice
+__device__ __forceinline__ long long clamp_cell(long long i, int dim) { return i < -1 ? -1 : (i > dim ? dim : i); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile sweep.  One CTA = one query tile (4x4x4 cells of the shared cell grid).  The 6x6x6 reference cells around it
+// are 36 contiguous x-runs of the cell-sorted reference cloud; each run is brought into shared memory with one TMA
+// bulk copy (raw 32-byte records), then re-expressed as fp32 offsets from the tile centre (error < 2e-7 h).  Every
+// thread owns one query of the tile and walks its own 3x3x3 window inside the staged region: candidates are screened
+// with fp32 arithmetic, and every candidate that could still be the nearest neighbour given the fp32 error bound is
+// re-evaluated in fp64 from the raw record with the reference's exact operation order.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kRegW = kTileEdge + 2;            // 6 cells per region row
+static constexpr int kRegRows = kRegW * kRegW;         // 36 rows
+static constexpr int kNNCap = 640;                     // staged candidates per tile (48 B each)
+static constexpr int kSegs = kTileEdge * kTileEdge;    // 16 query row segments per tile
+
+__global__ void __launch_bounds__(kTileThreads)
+nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lattice Lq,
+               const uint32_t *__restrict__ tiles, long long t_begin, const P4 *__restrict__ R,
+               const uint32_t *__restrict__ r_off, Lattice Lr, NNConst C, int32_t *__restrict__ nn_idx,
+               double *__restrict__ nn_d2, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count,
+               AccBlock *__restrict__ acc) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  P4 *raw = reinterpret_cast<P4 *>(smem_raw);
+  float4 *rel = reinterpret_cast<float4 *>(smem_raw + (size_t)kNNCap * sizeof(P4));
+  __shared__ uint32_t row_g0[kRegRows];                // global start of each region row
+  __shared__ uint32_t row_pref[kRegRows + 1];          // staged prefix
+  __shared__ uint16_t cell_rel[kRegRows][kRegW + 1];   // staged offset of each cell boundary inside its row
+  __shared__ uint32_t seg_g0[kSegs], seg_pref[kSegs + 1];
+  __shared__ __align__(8) uint64_t mbar;
+
+  const int tid = threadIdx.x;
+  const uint32_t tile = tiles[t_begin + blockIdx.x];
+  const int bx = (int)(tile % Lq.nb[0]), by = (int)((tile / Lq.nb[0]) % Lq.nb[1]), bz = (int)(tile / ((uint32_t)Lq.nb[0] * Lq.nb[1]));
+  // the two lattices share (v, m): reference cell = query cell + integer shift
+  const long long shx = (long long)(Lq.k_lo[0] - Lr.k_lo[0]) * Lq.m, shy = (long long)(Lq.k_lo[1] - Lr.k_lo[1]) * Lq.m,
+                  shz = (long long)(Lq.k_lo[2] - Lr.k_lo[2]) * Lq.m;
+  const long long r0x = (long long)bx * kTileEdge + shx - 1, r0y = (long long)by * kTileEdge + shy - 1,
+                  r0z = (long long)bz * kTileEdge + shz - 1;   // region origin in reference cells (may be outside)
+
+  if (tid == 0) mbar_init(&mbar, 1);
+  uint32_t my_cnt = 0;
+  if (tid < kRegRows) {
+    const long long y = r0y + tid % kRegW, z = r0z + tid / kRegW;
+    uint32_t g0 = 0;
+    const long long xa = max(r0x, 0ll), xb = min(r0x + kRegW - 1, (long long)Lr.dims[0] - 1);
+    bool ok = y >= 0 && y < Lr.dims[1] && z >= 0 && z < Lr.dims[2] && xa <= xb;
+    if (ok) {
+      const long long row = (z * Lr.dims[1] + y) * (long long)Lr.dims[0];
+      g0 = __ldg(r_off + row + xa);
+#pragma unroll
+      for (int c = 0; c <= kRegW; ++c) {
+        long long x = r0x + c;
+        x = x < xa ? xa : (x > xb + 1 ? xb + 1 : x);
+        cell_rel[tid][c] = (uint16_t)min(__ldg(r_off + row + x) - g0, 0xffffu);
+      }
+      my_cnt = __ldg(r_off + row + xb + 1) - g0;
+    } else {
+#pragma unroll
+      for (int c = 0; c <= kRegW; ++c) cell_rel[tid][c] = 0;
+    }
+    row_g0[tid] = g0;
+    row_pref[tid + 1] = my_cnt;
+  } else if (tid >= 64 && tid < 64 + kSegs) {
+    const int s = tid - 64;
+    const int y = by * kTileEdge + s % kTileEdge, z = bz * kTileEdge + s / kTileEdge;
+    uint32_t g0 = 0, n = 0;
+    if (y < Lq.dims[1] && z < Lq.dims[2]) {
+      const long long row = ((long long)z * Lq.dims[1] + y) * Lq.dims[0];
+      const int xa = bx * kTileEdge, xb = min(xa + kTileEdge, Lq.dims[0]);
+      g0 = __ldg(q_off + row + xa);
+      n = __ldg(q_off + row + xb) - g0;
+    }
+    seg_g0[s] = g0;
+    seg_pref[s + 1] = n;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    row_pref[0] = 0;
+    for (int r = 0; r < kRegRows; ++r) { const uint32_t c = row_pref[r + 1]; row_pref[r + 1] = run + c; run += c; }
+  } else if (tid == 32) {
+    uint32_t run = 0;
+    seg_pref[0] = 0;
+    for (int s = 0; s < kSegs; ++s) { const uint32_t c = seg_pref[s + 1]; seg_pref[s + 1] = run + c; run += c; }
+  }
+  __syncthreads();
+  const uint32_t nc = row_pref[kRegRows], nq = seg_pref[kSegs];
+  const bool staged = nc <= (uint32_t)kNNCap;
+  // tile centre (absolute coordinates) — origin of the fp32 offsets
+  const double ocx = ((double)Lq.k_lo[0] * Lq.v) + ((double)bx * kTileEdge + 0.5 * kTileEdge) * Lq.h;
+  const double ocy = ((double)Lq.k_lo[1] * Lq.v) + ((double)by * kTileEdge + 0.5 * kTileEdge) * Lq.h;
+  const double ocz = ((double)Lq.k_lo[2] * Lq.v) + ((double)bz * kTileEdge + 0.5 * kTileEdge) * Lq.h;
+  if (staged && nc > 0) {
+    if (tid == 0) mbar_expect_tx(&mbar, nc * (uint32_t)sizeof(P4));
+    if (tid < kRegRows && my_cnt > 0)
+      tma_bulk_g2s(raw + row_pref[tid], R + row_g0[tid], my_cnt * (uint32_t)sizeof(P4), &mbar);
+    mbar_wait(&mbar, 0);
+    for (uint32_t i = tid; i < nc; i += kTileThreads) {
+      const P4 p = raw[i];
+      rel[i] = make_float4((float)(p.x - ocx), (float)(p.y - ocy), (float)(p.z - ocz), 0.f);
+    }
+    __syncthreads();
+  }
+
+  // fp32 screening error: |rel| <= 3.5 h per axis -> representation error <= 2^-24 * 3.5 h per operand
+  const float eta = (float)(7.0 * 3.5 * Lq.h * 5.9604645e-8);   // generous bound on |d32 - d| of the offset VECTOR
   LocalAcc a;
   a.clear();
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = q_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < q_end; i += stride) {
-    const P4 q = load_p4(Q + i);
-    long long ix = cell_coord(q.x, L, 0), iy = cell_coord(q.y, L, 1), iz = cell_coord(q.z, L, 2);
-    ix = ix < -1 ? -1 : (ix > L.dims[0] ? L.dims[0] : ix);
-    iy = iy < -1 ? -1 : (iy > L.dims[1] ? L.dims[1] : iy);
-    iz = iz < -1 ? -1 : (iz > L.dims[2] ? L.dims[2] : iz);
-
-    double best = INFINITY;
-    long long bidx = 0x7fffffffffffffffll;
-    double bdx = 0, bdy = 0, bdz = 0;
-    const int x0 = (int)max(ix - 1, 0ll), x1 = (int)min(ix + 1, (long long)L.dims[0] - 1);
-    if (x0 <= x1) {
+  for (uint32_t qb = 0; qb < nq; qb += kTileThreads) {
+    const uint32_t qi = qb + tid;
+    if (qi >= nq) break;
+    int seg = 0;
+#pragma unroll
+    for (int s = 1; s < kSegs; ++s) seg += (qi >= seg_pref[s]) ? 1 : 0;
+    const uint32_t pos = seg_g0[seg] + (qi - seg_pref[seg]);
+    const P4 q = load_p4(Q + pos);
+    const int qcx = (int)(cell_of(q.idx) % (uint32_t)Lq.dims[0]);
+    const int lx = qcx - bx * kTileEdge + 1, ly = seg % kTileEdge + 1, lz = seg / kTileEdge + 1;   // region-local cell
+    Best b;
+    b.init();
+    if (staged) {
+      const float qx = (float)(q.x - ocx), qy = (float)(q.y - ocy), qz = (float)(q.z - ocz);
+      float thresh = INFINITY;
+#pragma unroll 1
       for (int dz = -1; dz <= 1; ++dz) {
-        long long z = iz + dz;
-        if (z < 0 || z >= L.dims[2]) continue;
+#pragma unroll 1
         for (int dy = -1; dy <= 1; ++dy) {
-          long long y = iy + dy;
-          if (y < 0 || y >= L.dims[1]) continue;
-          const long long row = (z * L.dims[1] + y) * (long long)L.dims[0];
-          uint32_t s = __ldg(cell_off + row + x0), e = __ldg(cell_off + row + x1 + 1);
-          for (uint32_t j = s; j < e; ++j) {
-            const P4 p = load_p4(R + j);
-            double ddx = __dsub_rn(q.x, p.x), ddy = __dsub_rn(q.y, p.y), ddz = __dsub_rn(q.z, p.z);
-            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-            if (d2 < best || (d2 == best && p.idx < bidx)) { best = d2; bidx = p.idx; bdx = ddx; bdy = ddy; bdz = ddz; }
+          const int rr = (lz + dz) * kRegW + (ly + dy);
+          const uint32_t base = row_pref[rr];
+          const uint32_t so = base + cell_rel[rr][lx - 1], eo = base + cell_rel[rr][lx + 2];
+          for (uint32_t j = so; j < eo; ++j) {
+            const float4 c = rel[j];
+            const float ddx = c.x - qx, ddy = c.y - qy, ddz = c.z - qz;
+            const float d32 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+            if (d32 <= thresh) {
+              const P4 p = raw[j];
+              if (b.offer(q, p.x, p.y, p.z, orig_of(p.idx))) {
+                const float bf = (float)b.d2;
+                // any candidate whose true distance is <= b.d2 has d32 <= b.d2 + E(b.d2); 1.5x for fp32 rounding
+                thresh = (bf + 1.5f * (2.f * sqrtf(bf) * eta + eta * eta + 1e-6f * bf)) * 1.0000005f + 1e-30f;
+              }
+            }
           }
         }
       }
+    } else {
+      search_block_global(q, r0x + lx, r0y + ly, r0z + lz, R, r_off, Lr, b);
     }
-    // is the best provably the global nearest neighbour?
-    double ux = cell_coord_cont(q.x, L, 0), uy = cell_coord_cont(q.y, L, 1), uz = cell_coord_cont(q.z, L, 2);
-    double g = fmin(fmin(face_dist_cells(ux, ix, 1, L.dims[0]), face_dist_cells(uy, iy, 1, L.dims[1])),
-                    face_dist_cells(uz, iz, 1, L.dims[2])) * L.h;
-    double slack = 1e-9 * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
-    double ge = g - slack;
-    double ge2 = ge > 0 ? ge * ge : 0.0;
-    bool resolved = best < ge2;
-    bool beyond = false;
-    if (!resolved && ge2 > C.max_d2) { resolved = true; beyond = best > C.max_d2; }   // nothing farther matters
-    if (!resolved) {
-      nn_idx[i] = best < INFINITY ? (int32_t)bidx : -1;
-      nn_d2[i] = best;
-      unsigned int slot = atomicAdd(far_count, 1u);
-      far_list[slot] = (uint32_t)(i - q_begin);
-      continue;
-    }
-    if (beyond || !(best < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; continue; }
-    nn_idx[i] = (int32_t)bidx;
-    nn_d2[i] = best;
-    if (C.want_full_cd) a.sum_nn += __dsqrt_rn(best);        // map_eval.cpp:1416
-    if (C.accumulate && keep_pair(best, C)) accum_pair(bdx, bdy, bdz, C, a);
+    // the searched block is centred on the query's own (unclamped) reference cell; the far kernel restarts from ring 0
+    finish_query(q, pos, r0x + lx, r0y + ly, r0z + lz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a);
   }
   flush_acc(a, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// far queries: one warp per query, Chebyshev rings r = 2, 3, ... until the best beats the block faces
+// far queries: one warp per query, Chebyshev rings r = 0, 1, 2, ... until the best beats the block faces
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-nn_far_kernel(const P4 *__restrict__ Q, long long q_begin, const P4 *__restrict__ R,
-              const uint32_t *__restrict__ cell_off, Lattice L, NNConst C, int32_t *__restrict__ nn_idx,
-              double *__restrict__ nn_d2, const uint32_t *__restrict__ far_list,
-              const unsigned int *__restrict__ far_count, AccBlock *__restrict__ acc) {
+nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, const uint32_t *__restrict__ cell_off, Lattice L,
+              NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
+              const uint32_t *__restrict__ far_list, const unsigned int *__restrict__ far_count,
+              AccBlock *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const unsigned int nfar = *far_count;
   for (long long w = warp; w < nfar; w += nwarps) {
-    const long long i = q_begin + far_list[w];
+    const long long i = far_list[w];
     const P4 q = load_p4(Q + i);
-    long long ix = cell_coord(q.x, L, 0), iy = cell_coord(q.y, L, 1), iz = cell_coord(q.z, L, 2);
-    ix = ix < -1 ? -1 : (ix > L.dims[0] ? L.dims[0] : ix);
-    iy = iy < -1 ? -1 : (iy > L.dims[1] ? L.dims[1] : iy);
-    iz = iz < -1 ? -1 : (iz > L.dims[2] ? L.dims[2] : iz);
+    const long long ix = clamp_cell(cell_coord(q.x, L, 0), L.dims[0]), iy = clamp_cell(cell_coord(q.y, L, 1), L.dims[1]),
+                    iz = clamp_cell(cell_coord(q.z, L, 2), L.dims[2]);
     const double ux = cell_coord_cont(q.x, L, 0), uy = cell_coord_cont(q.y, L, 1), uz = cell_coord_cont(q.z, L, 2);
     const double slack = 1e-9 * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
     double best = nn_d2[i];
-    long long bidx = nn_idx[i] >= 0 ? (long long)nn_idx[i] : 0x7fffffffffffffffll;
+    int bidx = nn_idx[i] >= 0 ? nn_idx[i] : 0x7fffffff;
     bool beyond = false;
-    for (int r = 2;; ++r) {
+    for (int r = 0;; ++r) {
       const int side = 2 * r + 1;
       // rows of the shell: every (dy,dz) in [-r,r]^2; border rows scan the full x range, inner rows two end cells
       for (int t = lane; t < side * side; t += 32) {
@@ -210,25 +365,26 @@ nn_far_kernel(const P4 *__restrict__ Q, long long q_begin, const P4 *__restrict_
           else { xa = xb = part ? ix + r : ix - r; }
           xa = max(xa, 0ll); xb = min(xb, (long long)L.dims[0] - 1);
           if (xa > xb) continue;
-          uint32_t s = __ldg(cell_off + row + xa), e = __ldg(cell_off + row + xb + 1);
+          const uint32_t s = __ldg(cell_off + row + xa), e = __ldg(cell_off + row + xb + 1);
           for (uint32_t j = s; j < e; ++j) {
             const P4 p = load_p4(R + j);
-            double d2 = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (d2 < best || (d2 == best && p.idx < bidx)) { best = d2; bidx = p.idx; }
+            const double d2 = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z);
+            const int pi = orig_of(p.idx);
+            if (d2 < best || (d2 == best && pi < bidx)) { best = d2; bidx = pi; }
           }
         }
       }
       // warp arg-min (distance, then smaller index)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
         if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
       }
-      double g = fmin(fmin(face_dist_cells(ux, ix, r, L.dims[0]), face_dist_cells(uy, iy, r, L.dims[1])),
-                      face_dist_cells(uz, iz, r, L.dims[2])) * L.h;
-      double ge = g - slack;
-      double ge2 = ge > 0 ? ge * ge : 0.0;
+      const double g = fmin(fmin(face_dist_cells(ux, ix, r, L.dims[0]), face_dist_cells(uy, iy, r, L.dims[1])),
+                            face_dist_cells(uz, iz, r, L.dims[2])) * L.h;
+      const double ge = g - slack;
+      const double ge2 = ge > 0 ? ge * ge : 0.0;
       if (best < ge2) break;
       if (ge2 > C.max_d2) { beyond = best > C.max_d2; break; }
       if (g == INFINITY) break;   // the block covers the whole lattice
@@ -237,7 +393,7 @@ nn_far_kernel(const P4 *__restrict__ Q, long long q_begin, const P4 *__restrict_
       atomicAdd(&acc->n_far, 1ull);
       if (beyond || !(best < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; }
       else {
-        nn_idx[i] = (int32_t)bidx;
+        nn_idx[i] = bidx;
         nn_d2[i] = best;
         if (C.want_full_cd) atomicAdd(&acc->sum_nn, __dsqrt_rn(best));
         // pair statistics of far queries: nn_far_accum_kernel (needs the winner's coordinates)
@@ -248,7 +404,7 @@ nn_far_kernel(const P4 *__restrict__ Q, long long q_begin, const P4 *__restrict_
 
 // far queries' pair statistics (the winner's coordinates come from the caller-order reference array)
 __global__ void __launch_bounds__(kThreads)
-nn_far_accum_kernel(const P4 *__restrict__ Q, long long q_begin, const double *__restrict__ ref_xyz, NNConst C,
+nn_far_accum_kernel(const P4 *__restrict__ Q, const double *__restrict__ ref_xyz, NNConst C,
                     const int32_t *__restrict__ nn_idx, const double *__restrict__ nn_d2,
                     const uint32_t *__restrict__ far_list, const unsigned int *__restrict__ far_count,
                     AccBlock *__restrict__ acc) {
@@ -256,13 +412,13 @@ nn_far_accum_kernel(const P4 *__restrict__ Q, long long q_begin, const double *_
   a.clear();
   const unsigned int nfar = *far_count;
   for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < nfar; w += (long long)gridDim.x * blockDim.x) {
-    const long long i = q_begin + far_list[w];
+    const long long i = far_list[w];
     const int32_t j = nn_idx[i];
     if (j < 0) continue;
     const double d2 = nn_d2[i];
     if (!keep_pair(d2, C)) continue;
     const P4 q = load_p4(Q + i);
-    double px = __ldg(ref_xyz + 3ll * j), py = __ldg(ref_xyz + 3ll * j + 1), pz = __ldg(ref_xyz + 3ll * j + 2);
+    const double px = __ldg(ref_xyz + 3ll * j), py = __ldg(ref_xyz + 3ll * j + 1), pz = __ldg(ref_xyz + 3ll * j + 2);
     accum_pair(__dsub_rn(q.x, px), __dsub_rn(q.y, py), __dsub_rn(q.z, pz), C, a);
   }
   flush_acc(a, acc);
@@ -271,41 +427,51 @@ nn_far_accum_kernel(const P4 *__restrict__ Q, long long q_begin, const double *_
 // ---------------------------------------------------------------------------------------------------------------
 // ME_PAIRING_AS_WRITTEN: map_eval.cpp:1233 stores (nn_est, i_gt); :1241 passes (source = gt, target = est), so
 // :1093-1094 reads gt[nn_est] and est[i_gt].  Reproduced verbatim; out-of-range (UB in the reference) is counted.
+// Walks every gt point; points this rank did not evaluate carry the marker -2.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-pair_as_written_kernel(const P4 *__restrict__ Qgt, long long q_begin, long long q_end,
-                       const int32_t *__restrict__ nn_idx, const double *__restrict__ nn_d2,
-                       const double *__restrict__ gt_xyz, long long n_gt, const double *__restrict__ est_xyz,
-                       long long n_est, NNConst C, AccBlock *__restrict__ acc) {
+pair_as_written_kernel(const P4 *__restrict__ Qgt, long long n, const int32_t *__restrict__ nn_idx,
+                       const double *__restrict__ nn_d2, const double *__restrict__ gt_xyz, long long n_gt,
+                       const double *__restrict__ est_xyz, long long n_est, NNConst C, AccBlock *__restrict__ acc) {
   LocalAcc a;
   a.clear();
-  for (long long i = q_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < q_end;
-       i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int32_t nn_est = nn_idx[i];
     if (nn_est < 0) continue;
     if (!keep_pair(nn_d2[i], C)) continue;
-    const long long i_gt = __double_as_longlong(__ldg(reinterpret_cast<const double *>(Qgt + i) + 3));
+    const long long i_gt = orig_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Qgt + i) + 3)));
     const long long s = nn_est, t = i_gt;          // source index into gt, target index into est
     if (s >= n_gt || t >= n_est) { a.n_ub++; continue; }
-    double dx = __dsub_rn(__ldg(gt_xyz + 3 * s), __ldg(est_xyz + 3 * t));
-    double dy = __dsub_rn(__ldg(gt_xyz + 3 * s + 1), __ldg(est_xyz + 3 * t + 1));
-    double dz = __dsub_rn(__ldg(gt_xyz + 3 * s + 2), __ldg(est_xyz + 3 * t + 2));
+    const double dx = __dsub_rn(__ldg(gt_xyz + 3 * s), __ldg(est_xyz + 3 * t));
+    const double dy = __dsub_rn(__ldg(gt_xyz + 3 * s + 1), __ldg(est_xyz + 3 * t + 1));
+    const double dz = __dsub_rn(__ldg(gt_xyz + 3 * s + 2), __ldg(est_xyz + 3 * t + 2));
     accum_pair(dx, dy, dz, C, a);
   }
   flush_acc(a, acc);
 }
 
+__global__ void fill_i32_kernel(int32_t *p, long long n, int32_t v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
 __global__ void fill_nn_kernel(int32_t *idx, double *d2, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     idx[i] = -1; d2[i] = NAN;
   }
 }
-__global__ void unsort_nn_kernel(const P4 *__restrict__ Q, long long b, long long e, const int32_t *__restrict__ sidx,
+__global__ void unsort_nn_kernel(const P4 *__restrict__ Q, long long n, const int32_t *__restrict__ sidx,
                                  const double *__restrict__ sd2, int32_t *__restrict__ oidx, double *__restrict__ od2) {
-  for (long long i = b + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < e; i += (long long)gridDim.x * blockDim.x) {
-    long long o = __double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + i) + 3));
-    oidx[o] = sidx[i]; od2[o] = sd2[i];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int32_t v = sidx[i];
+    if (v == -2) continue;    // not evaluated by this rank
+    const long long o = orig_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + i) + 3)));
+    oidx[o] = v; od2[o] = sd2[i];
   }
+}
+__global__ void count_marked_kernel(const int32_t *__restrict__ idx, long long n, unsigned long long *out) {
+  unsigned long long c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += idx[i] != -2;
+  c = (unsigned long long)warp_sum_ll((long long)c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -315,9 +481,8 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   Cloud &Qc = ctx->cloud[qwhich];
   Cloud &Rc = ctx->cloud[1 - qwhich];
   StageTimer timer(ctx, stage);
-  long long qb, qe;
-  shard_range(ctx, Qc.n, &qb, &qe);
-  const long long nq = qe - qb;
+  long long tb, te;
+  shard_range(ctx, Qc.n_tiles, &tb, &te);      // query tiles are sharded across ranks
 
   NNConst C;
   for (int k = 0; k < 5; ++k) C.tau[k] = p->tau[k];
@@ -332,39 +497,56 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
 
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_idx, &Qc.cap_nn, Qc.n, sizeof(int32_t)));
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_d2, &Qc.cap_nn_d2, Qc.n, sizeof(double)));
-  // work buffer: far list (nq uint32) after a 256-byte header holding the far counter
-  ME_TRY(ensure_work(ctx, 256 + (size_t)std::max<long long>(nq, 1) * sizeof(uint32_t)));
+  // work buffer: far list (n uint32) after a 256-byte header holding the far counter and the query counter
+  ME_TRY(ensure_work(ctx, 256 + (size_t)Qc.n * sizeof(uint32_t)));
   unsigned int *far_count = (unsigned int *)ctx->d_work;
+  unsigned long long *n_eval = (unsigned long long *)((char *)ctx->d_work + 64);
   uint32_t *far_list = (uint32_t *)((char *)ctx->d_work + 256);
   AccBlock *acc = (AccBlock *)ctx->d_scratch;
   ME_CUDA(ctx, cudaMemsetAsync(acc, 0, sizeof(AccBlock), ctx->stream));
-  ME_CUDA(ctx, cudaMemsetAsync(far_count, 0, sizeof(unsigned int), ctx->stream));
-
-  if (nq > 0) {
-    int blocks = (int)std::min<long long>((nq + kThreads - 1) / kThreads, (long long)ctx->sm_count * 32);
-    nn_sweep_kernel<<<blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, qb, qe, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C,
-                                                         Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
+  ME_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, 256, ctx->stream));
+  const int fill_blocks = (int)std::min<long long>((Qc.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  const bool sharded = ctx->world > 1;
+  if (sharded) {   // mark the queries other ranks own
+    fill_i32_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_nn_idx, Qc.n, -2);
     ME_LAUNCH_CHECK(ctx);
-    int fblocks = ctx->sm_count * 4;
-    nn_far_kernel<<<fblocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, qb, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C,
-                                                        Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
+  }
+  static bool attr_done = false;
+  const size_t dyn_smem = (size_t)kNNCap * (sizeof(P4) + sizeof(float4));
+  if (!attr_done) {
+    ME_CUDA(ctx, cudaFuncSetAttribute(nn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    attr_done = true;
+  }
+  if (te > tb) {
+    nn_tile_kernel<<<(unsigned)(te - tb), kTileThreads, dyn_smem, ctx->stream>>>(
+        Qc.d_sorted, Qc.d_cell_off, Qc.lat, Qc.d_tiles, tb, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C, Qc.d_nn_idx,
+        Qc.d_nn_d2, far_list, far_count, acc);
+    ME_LAUNCH_CHECK(ctx);
+    nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C,
+                                                                  Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
     ME_LAUNCH_CHECK(ctx);
     if (C.accumulate) {
-      nn_far_accum_kernel<<<ctx->sm_count, kThreads, 0, ctx->stream>>>(Qc.d_sorted, qb, Rc.d_xyz, C, Qc.d_nn_idx,
-                                                                       Qc.d_nn_d2, far_list, far_count, acc);
+      nn_far_accum_kernel<<<ctx->sm_count, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_xyz, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                       far_list, far_count, acc);
       ME_LAUNCH_CHECK(ctx);
     }
     if (as_written) {
-      pair_as_written_kernel<<<blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, qb, qe, Qc.d_nn_idx, Qc.d_nn_d2,
-                                                                  Qc.d_xyz, Qc.n, Rc.d_xyz, Rc.n, C, acc);
+      pair_as_written_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.n, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                       Qc.d_xyz, Qc.n, Rc.d_xyz, Rc.n, C, acc);
       ME_LAUNCH_CHECK(ctx);
     }
   }
+  if (sharded) {
+    count_marked_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_nn_idx, Qc.n, n_eval);
+    ME_LAUNCH_CHECK(ctx);
+  }
   AccBlock *h = (AccBlock *)ctx->h_pinned;
+  unsigned long long *h_eval = (unsigned long long *)((char *)ctx->h_pinned + 1024);
   ME_CUDA(ctx, cudaMemcpyAsync(h, acc, sizeof(AccBlock), cudaMemcpyDeviceToHost, ctx->stream));
+  if (sharded) ME_CUDA(ctx, cudaMemcpyAsync(h_eval, n_eval, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::memset(out, 0, sizeof(*out));
-  out->n_query = nq;
+  out->n_query = sharded ? (int64_t)*h_eval : Qc.n;
   out->n_corr = (int64_t)h->n_corr;
   for (int k = 0; k < 5; ++k) { out->n_inlier[k] = (int64_t)h->n_inl[k]; out->sum_d[k] = h->sum_d[k]; out->sum_d2[k] = h->sum_d2[k]; }
   out->n_ub = (int64_t)h->n_ub;
@@ -374,11 +556,20 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   return ME_OK;
 }
 
+int build_both(me_ctx *ctx) {
+  // a later build may re-plan the shared lattice and invalidate the earlier one: iterate to a fixed point
+  for (int it = 0; it < 3; ++it) {
+    ME_TRY(build_grid(ctx, ME_CLOUD_EST));
+    ME_TRY(build_grid(ctx, ME_CLOUD_GT));
+    if (ctx->cloud[0].grid_valid && ctx->cloud[1].grid_valid) return ME_OK;
+  }
+  return fail(ctx, ME_ERR_RANGE, "could not lay both clouds out on a common lattice");
+}
+
 int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e) {
   if (ctx->cloud[0].n <= 0 || ctx->cloud[1].n <= 0)
     return fail(ctx, ME_ERR_EMPTY, "both clouds must be set (map_eval.cpp:32-35)");
-  ME_TRY(build_grid(ctx, ME_CLOUD_EST));
-  ME_TRY(build_grid(ctx, ME_CLOUD_GT));
+  ME_TRY(build_both(ctx));
   const int dirs = p->directions ? p->directions : 3;
   if (e2g) std::memset(e2g, 0, sizeof(*e2g));
   if (g2e) std::memset(g2e, 0, sizeof(*g2e));
@@ -390,8 +581,6 @@ int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2
 int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2) {
   Cloud &Qc = ctx->cloud[which_query];
   if (!Qc.nn_valid) return fail(ctx, ME_ERR_INVALID, "me_get_nn before me_eval_nn");
-  long long qb, qe;
-  shard_range(ctx, Qc.n, &qb, &qe);
   size_t bytes = (size_t)Qc.n * (sizeof(int32_t) + sizeof(double)) + 256;
   ME_TRY(ensure_work(ctx, bytes));
   double *od2 = (double *)ctx->d_work;
@@ -399,10 +588,8 @@ int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2) {
   int blocks = (int)std::min<long long>((Qc.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
   fill_nn_kernel<<<blocks, kThreads, 0, ctx->stream>>>(oidx, od2, Qc.n);
   ME_LAUNCH_CHECK(ctx);
-  if (qe > qb) {
-    unsort_nn_kernel<<<blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, qb, qe, Qc.d_nn_idx, Qc.d_nn_d2, oidx, od2);
-    ME_LAUNCH_CHECK(ctx);
-  }
+  unsort_nn_kernel<<<blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.n, Qc.d_nn_idx, Qc.d_nn_d2, oidx, od2);
+  ME_LAUNCH_CHECK(ctx);
   if (h_idx) ME_CUDA(ctx, cudaMemcpyAsync(h_idx, oidx, (size_t)Qc.n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (h_d2) ME_CUDA(ctx, cudaMemcpyAsync(h_d2, od2, (size_t)Qc.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

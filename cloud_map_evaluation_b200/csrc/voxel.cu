@@ -333,8 +333,7 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
     if (c.grid_valid && c.lat.v != voxel_size) c.grid_valid = false;
   }
   ctx->voxel_hint = voxel_size;
-  ME_TRY(build_grid(ctx, ME_CLOUD_EST));
-  ME_TRY(build_grid(ctx, ME_CLOUD_GT));
+  ME_TRY(build_both(ctx));
   Cloud &E = ctx->cloud[ME_CLOUD_EST], &G = ctx->cloud[ME_CLOUD_GT];
   const Lattice Le = E.lat, Lg = G.lat;
   if (Le.nvoxels >= 0xffffffffll) return fail(ctx, ME_ERR_RANGE, "too many voxels");
