@@ -209,6 +209,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start: launch it early
     est, gt, cfg = synth.make_pair(args.config, scale=args.scale)
     n_est, n_gt = len(est), len(gt)
     p = A.make_nn_params(cfg["tau"], 1.0)        # path A as written + full CD
@@ -272,7 +273,6 @@ def main():
             ms = float(t.item())
         return ms / steps, ctx.launch_count() - l0, t0, t1
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         one_pass(False)
     stage_ms = {}

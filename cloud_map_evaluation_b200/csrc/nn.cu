@@ -191,7 +191,7 @@ static constexpr int kSegs = kTileEdge * kTileEdge;    // 16 query row segments 
 
 __global__ void __launch_bounds__(kTileThreads)
 nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lattice Lq,
-               const uint32_t *__restrict__ tiles, long long t_begin, const P4 *__restrict__ R,
+               const uint32_t *__restrict__ tiles, long long t_begin, long long t_end, const P4 *__restrict__ R,
                const uint32_t *__restrict__ r_off, Lattice Lr, NNConst C, int32_t *__restrict__ nn_idx,
                double *__restrict__ nn_d2, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count,
                AccBlock *__restrict__ acc) {
@@ -202,128 +202,162 @@ nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lat
   __shared__ uint32_t row_pref[kRegRows + 1];          // staged prefix
   __shared__ uint16_t cell_rel[kRegRows][kRegW + 1];   // staged offset of each cell boundary inside its row
   __shared__ uint32_t seg_g0[kSegs], seg_pref[kSegs + 1];
+  __shared__ uint32_t run_tab[9 * kTileThreads];       // per-thread window runs, [run][thread]
   __shared__ __align__(8) uint64_t mbar;
 
   const int tid = threadIdx.x;
-  const uint32_t tile = tiles[t_begin + blockIdx.x];
-  const int bx = (int)(tile % Lq.nb[0]), by = (int)((tile / Lq.nb[0]) % Lq.nb[1]), bz = (int)(tile / ((uint32_t)Lq.nb[0] * Lq.nb[1]));
   // the two lattices share (v, m): reference cell = query cell + integer shift
   const long long shx = (long long)(Lq.k_lo[0] - Lr.k_lo[0]) * Lq.m, shy = (long long)(Lq.k_lo[1] - Lr.k_lo[1]) * Lq.m,
                   shz = (long long)(Lq.k_lo[2] - Lr.k_lo[2]) * Lq.m;
-  const long long r0x = (long long)bx * kTileEdge + shx - 1, r0y = (long long)by * kTileEdge + shy - 1,
-                  r0z = (long long)bz * kTileEdge + shz - 1;   // region origin in reference cells (may be outside)
-
+  // fp32 screening error: |offset| <= 3.5 h per axis -> representation error <= 2^-24 * 3.5 h per operand; eta bounds
+  // the error of the difference VECTOR with a generous factor
+  const float eta = (float)(7.0 * 3.5 * Lq.h * 5.9604645e-8);
   if (tid == 0) mbar_init(&mbar, 1);
-  uint32_t my_cnt = 0;
-  if (tid < kRegRows) {
-    const long long y = r0y + tid % kRegW, z = r0z + tid / kRegW;
-    uint32_t g0 = 0;
-    const long long xa = max(r0x, 0ll), xb = min(r0x + kRegW - 1, (long long)Lr.dims[0] - 1);
-    bool ok = y >= 0 && y < Lr.dims[1] && z >= 0 && z < Lr.dims[2] && xa <= xb;
-    if (ok) {
-      const long long row = (z * Lr.dims[1] + y) * (long long)Lr.dims[0];
-      g0 = __ldg(r_off + row + xa);
-#pragma unroll
-      for (int c = 0; c <= kRegW; ++c) {
-        long long x = r0x + c;
-        x = x < xa ? xa : (x > xb + 1 ? xb + 1 : x);
-        cell_rel[tid][c] = (uint16_t)min(__ldg(r_off + row + x) - g0, 0xffffu);
-      }
-      my_cnt = __ldg(r_off + row + xb + 1) - g0;
-    } else {
-#pragma unroll
-      for (int c = 0; c <= kRegW; ++c) cell_rel[tid][c] = 0;
-    }
-    row_g0[tid] = g0;
-    row_pref[tid + 1] = my_cnt;
-  } else if (tid >= 64 && tid < 64 + kSegs) {
-    const int s = tid - 64;
-    const int y = by * kTileEdge + s % kTileEdge, z = bz * kTileEdge + s / kTileEdge;
-    uint32_t g0 = 0, n = 0;
-    if (y < Lq.dims[1] && z < Lq.dims[2]) {
-      const long long row = ((long long)z * Lq.dims[1] + y) * Lq.dims[0];
-      const int xa = bx * kTileEdge, xb = min(xa + kTileEdge, Lq.dims[0]);
-      g0 = __ldg(q_off + row + xa);
-      n = __ldg(q_off + row + xb) - g0;
-    }
-    seg_g0[s] = g0;
-    seg_pref[s + 1] = n;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t run = 0;
-    row_pref[0] = 0;
-    for (int r = 0; r < kRegRows; ++r) { const uint32_t c = row_pref[r + 1]; row_pref[r + 1] = run + c; run += c; }
-  } else if (tid == 32) {
-    uint32_t run = 0;
-    seg_pref[0] = 0;
-    for (int s = 0; s < kSegs; ++s) { const uint32_t c = seg_pref[s + 1]; seg_pref[s + 1] = run + c; run += c; }
-  }
-  __syncthreads();
-  const uint32_t nc = row_pref[kRegRows], nq = seg_pref[kSegs];
-  const bool staged = nc <= (uint32_t)kNNCap;
-  // tile centre (absolute coordinates) — origin of the fp32 offsets
-  const double ocx = ((double)Lq.k_lo[0] * Lq.v) + ((double)bx * kTileEdge + 0.5 * kTileEdge) * Lq.h;
-  const double ocy = ((double)Lq.k_lo[1] * Lq.v) + ((double)by * kTileEdge + 0.5 * kTileEdge) * Lq.h;
-  const double ocz = ((double)Lq.k_lo[2] * Lq.v) + ((double)bz * kTileEdge + 0.5 * kTileEdge) * Lq.h;
-  if (staged && nc > 0) {
-    if (tid == 0) mbar_expect_tx(&mbar, nc * (uint32_t)sizeof(P4));
-    if (tid < kRegRows && my_cnt > 0)
-      tma_bulk_g2s(raw + row_pref[tid], R + row_g0[tid], my_cnt * (uint32_t)sizeof(P4), &mbar);
-    mbar_wait(&mbar, 0);
-    for (uint32_t i = tid; i < nc; i += kTileThreads) {
-      const P4 p = raw[i];
-      rel[i] = make_float4((float)(p.x - ocx), (float)(p.y - ocy), (float)(p.z - ocz), 0.f);
-    }
-    __syncthreads();
-  }
-
-  // fp32 screening error: |rel| <= 3.5 h per axis -> representation error <= 2^-24 * 3.5 h per operand
-  const float eta = (float)(7.0 * 3.5 * Lq.h * 5.9604645e-8);   // generous bound on |d32 - d| of the offset VECTOR
+  uint32_t phase = 0;
   LocalAcc a;
   a.clear();
-  for (uint32_t qb = 0; qb < nq; qb += kTileThreads) {
-    const uint32_t qi = qb + tid;
-    if (qi >= nq) break;
-    int seg = 0;
+
+  for (long long t = t_begin + blockIdx.x; t < t_end; t += gridDim.x) {
+    const uint32_t tile = tiles[t];
+    const int bx = (int)(tile % Lq.nb[0]), by = (int)((tile / Lq.nb[0]) % Lq.nb[1]), bz = (int)(tile / ((uint32_t)Lq.nb[0] * Lq.nb[1]));
+    const long long r0x = (long long)bx * kTileEdge + shx - 1, r0y = (long long)by * kTileEdge + shy - 1,
+                    r0z = (long long)bz * kTileEdge + shz - 1;   // region origin in reference cells (may be outside)
+    uint32_t my_cnt = 0;
+    if (tid < kRegRows) {
+      const long long y = r0y + tid % kRegW, z = r0z + tid / kRegW;
+      uint32_t g0 = 0;
+      const long long xa = max(r0x, 0ll), xb = min(r0x + kRegW - 1, (long long)Lr.dims[0] - 1);
+      if (y >= 0 && y < Lr.dims[1] && z >= 0 && z < Lr.dims[2] && xa <= xb) {
+        const long long row = (z * Lr.dims[1] + y) * (long long)Lr.dims[0];
+        g0 = __ldg(r_off + row + xa);
 #pragma unroll
-    for (int s = 1; s < kSegs; ++s) seg += (qi >= seg_pref[s]) ? 1 : 0;
-    const uint32_t pos = seg_g0[seg] + (qi - seg_pref[seg]);
-    const P4 q = load_p4(Q + pos);
-    const int qcx = (int)(cell_of(q.idx) % (uint32_t)Lq.dims[0]);
-    const int lx = qcx - bx * kTileEdge + 1, ly = seg % kTileEdge + 1, lz = seg / kTileEdge + 1;   // region-local cell
-    Best b;
-    b.init();
-    if (staged) {
-      const float qx = (float)(q.x - ocx), qy = (float)(q.y - ocy), qz = (float)(q.z - ocz);
-      float thresh = INFINITY;
-#pragma unroll 1
-      for (int dz = -1; dz <= 1; ++dz) {
-#pragma unroll 1
-        for (int dy = -1; dy <= 1; ++dy) {
-          const int rr = (lz + dz) * kRegW + (ly + dy);
+        for (int c = 0; c <= kRegW; ++c) {
+          long long x = r0x + c;
+          x = x < xa ? xa : (x > xb + 1 ? xb + 1 : x);
+          cell_rel[tid][c] = (uint16_t)min(__ldg(r_off + row + x) - g0, 0xffffu);
+        }
+        my_cnt = __ldg(r_off + row + xb + 1) - g0;
+      } else {
+#pragma unroll
+        for (int c = 0; c <= kRegW; ++c) cell_rel[tid][c] = 0;
+      }
+      row_g0[tid] = g0;
+    } else if (tid >= 64 && tid < 64 + kSegs) {
+      const int s = tid - 64;
+      const int y = by * kTileEdge + s % kTileEdge, z = bz * kTileEdge + s / kTileEdge;
+      uint32_t g0 = 0, n = 0;
+      if (y < Lq.dims[1] && z < Lq.dims[2]) {
+        const long long row = ((long long)z * Lq.dims[1] + y) * Lq.dims[0];
+        const int xa = bx * kTileEdge, xb = min(xa + kTileEdge, Lq.dims[0]);
+        g0 = __ldg(q_off + row + xa);
+        n = __ldg(q_off + row + xb) - g0;
+      }
+      seg_g0[s] = g0;
+      my_cnt = n;
+    }
+    // warp-level exclusive scans: warps 0-1 hold the 36 region rows, warp 2 the 16 query segments
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+      uint32_t inc = my_cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      if (warp == 0) { row_pref[tid + 1] = inc; if (lane == 0) row_pref[0] = 0; }
+      __syncthreads();
+      if (warp == 1 && tid < kRegRows) row_pref[tid + 1] = inc + row_pref[32];
+      if (warp == 2) { if (lane < kSegs) seg_pref[lane + 1] = inc; if (lane == 0) seg_pref[0] = 0; }
+      __syncthreads();
+    }
+    const uint32_t nc = row_pref[kRegRows], nq = seg_pref[kSegs];
+    const bool staged = nc <= (uint32_t)kNNCap;
+    // tile centre (absolute coordinates) — origin of the fp32 offsets
+    const double ocx = ((double)Lq.k_lo[0] * Lq.v) + ((double)bx * kTileEdge + 0.5 * kTileEdge) * Lq.h;
+    const double ocy = ((double)Lq.k_lo[1] * Lq.v) + ((double)by * kTileEdge + 0.5 * kTileEdge) * Lq.h;
+    const double ocz = ((double)Lq.k_lo[2] * Lq.v) + ((double)bz * kTileEdge + 0.5 * kTileEdge) * Lq.h;
+    if (staged && nc > 0) {
+      if (tid == 0) mbar_expect_tx(&mbar, nc * (uint32_t)sizeof(P4));
+      if (tid < kRegRows && my_cnt > 0)
+        tma_bulk_g2s(raw + row_pref[tid], R + row_g0[tid], my_cnt * (uint32_t)sizeof(P4), &mbar);
+      mbar_wait(&mbar, phase);
+      phase ^= 1u;
+      for (uint32_t i = tid; i < nc; i += kTileThreads) {
+        const P4 p = raw[i];
+        rel[i] = make_float4((float)(p.x - ocx), (float)(p.y - ocy), (float)(p.z - ocz), 0.f);
+      }
+      __syncthreads();
+    }
+
+    for (uint32_t qb = 0; qb < nq; qb += kTileThreads) {
+      const uint32_t qi = qb + tid;
+      if (qi >= nq) break;
+      int seg = 0;
+#pragma unroll
+      for (int s = 1; s < kSegs; ++s) seg += (qi >= seg_pref[s]) ? 1 : 0;
+      const uint32_t pos = seg_g0[seg] + (qi - seg_pref[seg]);
+      const P4 q = load_p4(Q + pos);
+      const int qcx = (int)(cell_of(q.idx) % (uint32_t)Lq.dims[0]);
+      const int lx = qcx - bx * kTileEdge + 1, ly = seg % kTileEdge + 1, lz = seg / kTileEdge + 1;   // region-local cell
+      Best b;
+      b.init();
+      if (staged) {
+        const float qx = (float)(q.x - ocx), qy = (float)(q.y - ocy), qz = (float)(q.z - ocz);
+        // per-thread run table: the (up to 9) non-empty window runs of this query, packed start | end << 16
+        int nrun = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const int rr = (lz + r / 3 - 1) * kRegW + (ly + r % 3 - 1);
           const uint32_t base = row_pref[rr];
           const uint32_t so = base + cell_rel[rr][lx - 1], eo = base + cell_rel[rr][lx + 2];
-          for (uint32_t j = so; j < eo; ++j) {
-            const float4 c = rel[j];
-            const float ddx = c.x - qx, ddy = c.y - qy, ddz = c.z - qz;
-            const float d32 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-            if (d32 <= thresh) {
-              const P4 p = raw[j];
-              if (b.offer(q, p.x, p.y, p.z, orig_of(p.idx))) {
-                const float bf = (float)b.d2;
-                // any candidate whose true distance is <= b.d2 has d32 <= b.d2 + E(b.d2); 1.5x for fp32 rounding
-                thresh = (bf + 1.5f * (2.f * sqrtf(bf) * eta + eta * eta + 1e-6f * bf)) * 1.0000005f + 1e-30f;
+          if (eo > so) { run_tab[nrun * kTileThreads + tid] = so | (eo << 16); ++nrun; }
+        }
+        // pass 1, fp32 only: smallest and second smallest screened distance, the runs walked as ONE flattened loop
+        // so that the lanes of a warp stay in step
+        float b1 = INFINITY, b2 = INFINITY;
+        uint32_t j1 = 0, j = 0, e = 0;
+        int r = 0;
+        for (;;) {
+          if (j >= e) {
+            if (r >= nrun) break;
+            const uint32_t pk = run_tab[r * kTileThreads + tid];
+            ++r;
+            j = pk & 0xffffu; e = pk >> 16;
+          }
+          const float4 c = rel[j];
+          const float ddx = c.x - qx, ddy = c.y - qy, ddz = c.z - qz;
+          const float d32 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+          const bool lt = d32 < b1;
+          b2 = fminf(b2, lt ? b1 : d32);
+          j1 = lt ? j : j1;
+          b1 = fminf(b1, d32);
+          ++j;
+        }
+        if (b1 < INFINITY) {
+          // every candidate whose true distance is <= that of j1 has d32 <= b1 + 2 E(b1); 1.5x for fp32 rounding
+          const float lim = (b1 + 3.0f * (2.f * sqrtf(b1) * eta + eta * eta + 1e-6f * b1)) * 1.0000005f + 1e-30f;
+          if (b2 > lim) {
+            const P4 p = raw[j1];
+            b.offer(q, p.x, p.y, p.z, orig_of(p.idx));
+          } else {
+            // near-tie (or duplicate points): settle it in fp64 with the reference's operation order
+            for (int rr9 = 0; rr9 < nrun; ++rr9) {
+              const uint32_t pk = run_tab[rr9 * kTileThreads + tid];
+              for (uint32_t jj = pk & 0xffffu; jj < (pk >> 16); ++jj) {
+                const float4 c = rel[jj];
+                const float ddx = c.x - qx, ddy = c.y - qy, ddz = c.z - qz;
+                if (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= lim) {
+                  const P4 p = raw[jj];
+                  b.offer(q, p.x, p.y, p.z, orig_of(p.idx));
+                }
               }
             }
           }
         }
+      } else {
+        search_block_global(q, r0x + lx, r0y + ly, r0z + lz, R, r_off, Lr, b);
       }
-    } else {
-      search_block_global(q, r0x + lx, r0y + ly, r0z + lz, R, r_off, Lr, b);
+      // the searched block is centred on the query's own (unclamped) reference cell; the far kernel restarts from ring 0
+      finish_query(q, pos, r0x + lx, r0y + ly, r0z + lz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a);
     }
-    // the searched block is centred on the query's own (unclamped) reference cell; the far kernel restarts from ring 0
-    finish_query(q, pos, r0x + lx, r0y + ly, r0z + lz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a);
+    __syncthreads();   // shared tables and the staged region are re-used by the next tile
   }
   flush_acc(a, acc);
 }
@@ -518,8 +552,10 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     attr_done = true;
   }
   if (te > tb) {
-    nn_tile_kernel<<<(unsigned)(te - tb), kTileThreads, dyn_smem, ctx->stream>>>(
-        Qc.d_sorted, Qc.d_cell_off, Qc.lat, Qc.d_tiles, tb, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C, Qc.d_nn_idx,
+    // persistent CTAs: each walks tiles tb + blockIdx.x, + gridDim.x, ... and flushes its accumulators once
+    const unsigned grid = (unsigned)std::min<long long>(te - tb, (long long)ctx->sm_count * 16);
+    nn_tile_kernel<<<grid, kTileThreads, dyn_smem, ctx->stream>>>(
+        Qc.d_sorted, Qc.d_cell_off, Qc.lat, Qc.d_tiles, tb, te, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C, Qc.d_nn_idx,
         Qc.d_nn_d2, far_list, far_count, acc);
     ME_LAUNCH_CHECK(ctx);
     nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C,
