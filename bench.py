@@ -145,41 +145,6 @@ def run_reference(args):
     }))
 
 
-def _allreduce_accs(dist, torch, dev, nn_e, nn_g, mme_list):
-    """One SUM all-reduce over the int64 block, one over the fp64 block, one MIN/MAX pair for the entropy extrema."""
-    ints, flts, mins, maxs = [], [], [], []
-    for a in (nn_e, nn_g):
-        ints += [a.n_query, a.n_corr] + list(a.n_inlier) + [a.n_ub, a.n_far]
-        flts += list(a.sum_d) + list(a.sum_d2) + [a.sum_d_all, a.sum_d2_all, a.sum_nn_dist]
-    for m in mme_list:
-        ints += [m.n_query, m.n_valid]
-        flts += [m.sum_entropy]
-        mins.append(m.min_entropy); maxs.append(m.max_entropy)
-    ti = torch.tensor(ints, dtype=torch.int64, device=dev)
-    tf = torch.tensor(flts, dtype=torch.float64, device=dev)
-    dist.all_reduce(ti); dist.all_reduce(tf)
-    if mins:
-        tmin = torch.tensor(mins, dtype=torch.float64, device=dev)
-        tmax = torch.tensor(maxs, dtype=torch.float64, device=dev)
-        dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ti, tf = ti.cpu().tolist(), tf.cpu().tolist()
-    ii = fi = 0
-    for a in (nn_e, nn_g):
-        a.n_query, a.n_corr = ti[ii], ti[ii + 1]
-        for k in range(5):
-            a.n_inlier[k] = ti[ii + 2 + k]
-        a.n_ub, a.n_far = ti[ii + 7], ti[ii + 8]
-        ii += 9
-        for k in range(5):
-            a.sum_d[k] = tf[fi + k]; a.sum_d2[k] = tf[fi + 5 + k]
-        a.sum_d_all, a.sum_d2_all, a.sum_nn_dist = tf[fi + 10], tf[fi + 11], tf[fi + 12]
-        fi += 13
-    for j, m in enumerate(mme_list):
-        m.n_query, m.n_valid = ti[ii], ti[ii + 1]; ii += 2
-        m.sum_entropy = tf[fi]; fi += 1
-        m.min_entropy, m.max_entropy = float(tmin[j]), float(tmax[j])
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,6 +163,7 @@ def main():
     import torch
     import torch.distributed as dist
     from cloud_map_evaluation_b200 import api
+    from cloud_map_evaluation_b200 import dist as mdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -242,7 +208,7 @@ def main():
         nn_e, nn_g = ctx.eval_nn_accum(p)
         awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5) if cfg["awd"] else None
         if world > 1:
-            _allreduce_accs(dist, torch, dev, nn_e, nn_g, mmes)
+            mdist.allreduce_accumulators(nn_e, nn_g, mmes, device=dev)
         results["nn"] = ctx.nn_finalize(p, nn_e, nn_g)
         results["mme"] = [ctx.mme_finalize(m, w) for m, w in zip(mmes, (A.ME_CLOUD_EST, A.ME_CLOUD_GT))]
         results["awd"] = awd

@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing: one process per GPU, the evaluated cloud's query tiles/ranges sharded by rank, both lattices
+replicated, and ONE all-reduce of the sum-reducible accumulators (plus a MIN/MAX pair for the entropy extrema).
+
+The reference is single-process; this is the B200-native equivalent of its TBB/OpenMP reductions
+(map_eval.cpp:1411,1420,1704-1708).  torch.distributed is used for the collectives only: backend "nccl" on GPUs
+(NVLink 5 / NVSwitch), "gloo" in the CPU tests.
+"""
+from . import _abi as A
+
+_NN_I = A.ME_NN_ACCUM_I64
+_NN_F = A.ME_NN_ACCUM_F64
+
+
+def pack(nn_e, nn_g, mme_list):
+    """Flatten the accumulators into (int64 list, fp64 list, min list, max list)."""
+    ints, flts, mins, maxs = [], [], [], []
+    for a in (nn_e, nn_g):
+        ints += [a.n_query, a.n_corr] + list(a.n_inlier) + [a.n_ub, a.n_far]
+        flts += list(a.sum_d) + list(a.sum_d2) + [a.sum_d_all, a.sum_d2_all, a.sum_nn_dist]
+    for m in mme_list:
+        ints += [m.n_query, m.n_valid]
+        flts += [m.sum_entropy]
+        mins.append(m.min_entropy)
+        maxs.append(m.max_entropy)
+    return ints, flts, mins, maxs
+
+
+def unpack(ints, flts, mins, maxs, nn_e, nn_g, mme_list):
+    ii = fi = 0
+    for a in (nn_e, nn_g):
+        a.n_query, a.n_corr = int(ints[ii]), int(ints[ii + 1])
+        for k in range(5):
+            a.n_inlier[k] = int(ints[ii + 2 + k])
+        a.n_ub, a.n_far = int(ints[ii + 7]), int(ints[ii + 8])
+        ii += _NN_I
+        for k in range(5):
+            a.sum_d[k] = float(flts[fi + k])
+            a.sum_d2[k] = float(flts[fi + 5 + k])
+        a.sum_d_all, a.sum_d2_all, a.sum_nn_dist = float(flts[fi + 10]), float(flts[fi + 11]), float(flts[fi + 12])
+        fi += _NN_F
+    for j, m in enumerate(mme_list):
+        m.n_query, m.n_valid = int(ints[ii]), int(ints[ii + 1])
+        ii += 2
+        m.sum_entropy = float(flts[fi])
+        fi += 1
+        m.min_entropy, m.max_entropy = float(mins[j]), float(maxs[j])
+
+
+def allreduce_accumulators(nn_e, nn_g, mme_list, device=None, group=None):
+    """In-place all-reduce of the partial accumulators of every rank.  Integer counts are order-independent, so the
+    reduced inlier counts are bit-exact for any world size; fp64 sums differ from the 1-GPU run by rounding only."""
+    import torch
+    import torch.distributed as dist
+    ints, flts, mins, maxs = pack(nn_e, nn_g, mme_list)
+    ti = torch.tensor(ints, dtype=torch.int64, device=device)
+    tf = torch.tensor(flts, dtype=torch.float64, device=device)
+    dist.all_reduce(ti, group=group)
+    dist.all_reduce(tf, group=group)
+    tmin = tmax = None
+    if mins:
+        tmin = torch.tensor(mins, dtype=torch.float64, device=device)
+        tmax = torch.tensor(maxs, dtype=torch.float64, device=device)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX, group=group)
+    unpack(ti.cpu().tolist(), tf.cpu().tolist(), tmin.cpu().tolist() if mins else [], tmax.cpu().tolist() if mins else [],
+           nn_e, nn_g, mme_list)
+
+
+def shard_range(n, rank, world):
+    """The contiguous range a rank owns — the same rule as libmapeval_b200 (common.cuh shard_range)."""
+    return n * rank // world, n * (rank + 1) // world
