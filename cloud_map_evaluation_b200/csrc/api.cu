@@ -52,6 +52,7 @@ static void invalidate(Cloud &c) {
 static void free_cloud(Cloud &c) {
   if (c.owned && c.d_xyz) cudaFree(c.d_xyz);
   if (c.d_sorted) cudaFree(c.d_sorted);
+  if (c.d_rel) cudaFree(c.d_rel);
   if (c.d_cell_off) cudaFree(c.d_cell_off);
   if (c.d_cell_id) cudaFree(c.d_cell_id);
   if (c.d_nn_idx) cudaFree(c.d_nn_idx);

@@ -47,6 +47,8 @@ struct Cloud {
   Lattice lat;
   P4 *d_sorted = nullptr;       // cell-sorted points
   long long cap_sorted = 0;
+  float4 *d_rel = nullptr;      // cell-sorted fp32 screening copy: xyz relative to the point's own cell origin, w = (float)ix
+  long long cap_rel = 0;
   uint32_t *d_cell_off = nullptr;   // ncells + 1 CSR offsets into d_sorted: cell c = [off[c], off[c+1])
   long long cap_cells = 0;
   uint32_t *d_cell_id = nullptr;    // scratch: cell of each point (caller order)
@@ -54,6 +56,7 @@ struct Cloud {
   uint32_t *d_tiles = nullptr;      // non-empty query tiles (tile id = (bz*nb[1]+by)*nb[0]+bx)
   long long cap_tiles = 0;
   long long n_tiles = 0;
+  long long max_cell_count = 0;     // points in the fullest cell
   cudaEvent_t upload_done = nullptr;  // recorded on the copy stream after me_set_cloud's H2D
   bool upload_pending = false;
   // per-query results, SORTED order of this cloud (unsorted on demand)
@@ -177,6 +180,14 @@ __device__ __forceinline__ long long cell_coord(double x, const Lattice &L, int 
 // continuous cell coordinate (for face distances)
 __device__ __forceinline__ double cell_coord_cont(double x, const Lattice &L, int axis) {
   return (x - (double)L.k_lo[axis] * L.v) / L.h;
+}
+
+// offset of coordinate x from the origin of lattice cell `ic` on `axis` (fp64; the caller rounds it to fp32).
+// Origin = (k_lo + ic / m) * v + (ic % m) * h, the same products cell_coord() forms, so |offset| < ~h.
+__device__ __forceinline__ double cell_rel(double x, uint32_t ic, const Lattice &L, int axis) {
+  const uint32_t kv = ic / (uint32_t)L.m, s = ic - kv * (uint32_t)L.m;
+  const double fx = __dsub_rn(x, __dmul_rn((double)(L.k_lo[axis] + (int)kv), L.v));
+  return fx - (double)s * L.h;
 }
 
 __device__ __forceinline__ P4 load_p4(const P4 *p) {

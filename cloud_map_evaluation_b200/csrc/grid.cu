@@ -217,6 +217,21 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const double *__restr
   }
 }
 
+// fp32 screening copy of the sorted cloud (streaming pass, coalesced both ways): offset of every point from the origin
+// of its own cell (|offset| < ~h, so the fp32 rounding error is ~3e-8 h whatever the world extent) and the cell's x
+// index.  The sweeps rebuild the offset between two points as (ix_a - ix_b) * h + (rel_a - rel_b).
+__global__ void __launch_bounds__(kThreads) rel_kernel(const P4 *__restrict__ sorted, long long n, Lattice L,
+                                                       float4 *__restrict__ rel) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const P4 p = load_p4(sorted + i);
+    const uint32_t c = cell_of(p.idx);
+    const uint32_t ix = c % (uint32_t)L.dims[0];
+    const uint32_t cyz = c / (uint32_t)L.dims[0];
+    const uint32_t iy = cyz % (uint32_t)L.dims[1], iz = cyz / (uint32_t)L.dims[1];
+    rel[i] = make_float4((float)cell_rel(p.x, ix, L, 0), (float)cell_rel(p.y, iy, L, 1), (float)cell_rel(p.z, iz, L, 2), (float)ix);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // query tiles: every kTileEdge^3 block of cells that holds at least one point (from the histogram, before the scan)
 // ---------------------------------------------------------------------------------------------------------------
@@ -379,15 +394,19 @@ int build_grid(me_ctx *ctx, int which) {
   // non-empty query tiles, from the histogram
   const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
   ME_TRY(ensure(ctx, (void **)&c.d_tiles, &c.cap_tiles, std::min<long long>(nt, c.n), sizeof(uint32_t)));
+  // scratch slots: [8] number of tiles, [9] occupied cells, [10] largest cell (bounds the run lengths of the sweeps)
   unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
-  ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), ctx->stream));
+  ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, 3 * sizeof(unsigned long long), ctx->stream));
   {
     int blocks = (int)std::min<long long>((nt + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
     tile_list_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L, c.d_tiles, d_nt);
     ME_LAUNCH_CHECK(ctx);
+    blocks = (int)std::min<long long>((L.ncells + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+    occupancy_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, d_nt + 1);
+    ME_LAUNCH_CHECK(ctx);
   }
   unsigned long long *h_nt = (unsigned long long *)ctx->h_pinned + 8;
-  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 
   // exclusive scan of the histogram, in place
   long long ntiles = (L.ncells + kScanTile - 1) / kScanTile;
@@ -401,11 +420,15 @@ int build_grid(me_ctx *ctx, int which) {
   ME_LAUNCH_CHECK(ctx);
 
   ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, c.n, sizeof(P4)));
+  ME_TRY(ensure(ctx, (void **)&c.d_rel, &c.cap_rel, c.n, sizeof(float4)));
   int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
   scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
   ME_LAUNCH_CHECK(ctx);
+  rel_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.n, L, c.d_rel);
+  ME_LAUNCH_CHECK(ctx);
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  c.n_tiles = (long long)*h_nt;
+  c.n_tiles = (long long)h_nt[0];
+  c.max_cell_count = (long long)h_nt[2];
   c.grid_valid = true;
   c.nn_valid = false;
   c.entropy_valid = false;

@@ -18,7 +18,9 @@
 // neighbours per query the accept path needs the exact fp64 record of nearly every candidate, so the shared-memory
 // pipe (random 32-byte reads, bank conflicts) becomes the limiter instead of L1.
 #include "common.cuh"
+#include "flat.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace me {
@@ -153,6 +155,153 @@ mme_kernel(const P4 *__restrict__ S, long long q_begin, long long q_end, const u
   flush_stats(ts, acc);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// flat kernel (rings <= 3): the dominant kernel of the pass.
+//
+// One thread per query, queries in cell-sorted order.  Per query the (2R+1)^2 lattice rows of the neighbourhood are
+// pruned against the sphere with a handful of fp32 compares (no sqrt: the x-extent of a row is found by comparing the
+// row's remaining squared radius against the 2R per-query squared gaps to the neighbouring cell faces), and the
+// surviving x-runs are written to a per-thread run table in shared memory ([row][thread], conflict-free).  The
+// candidates are then walked as ONE flattened loop, so that the 32 lanes of a warp — neighbours along x, hence with
+// near-identical run tables — stay in step whatever the occupancy of the individual rows.
+//
+// Candidates are screened in fp32 on the cell-relative copy of the cloud (Cloud::d_rel, 16 B/point): the offset
+// between two points is rebuilt as (ix_c - ix_q) h + (rel_c - rel_q), whose error is ~1e-6 h independent of the world
+// extent.  A candidate whose fp32 d^2 falls inside the error band around r^2 is decided exactly, in fp64, from the
+// raw records with the reference's operation order (nanoflann: d2 < r2, strict), so the neighbour COUNT — and with it
+// the k >= min_neighbors validity test — is bit-exact.  Accepted offsets are accumulated in fp64.
+// ---------------------------------------------------------------------------------------------------------------
+struct MmeConst {
+  float h, inv_h;            // cell edge and its inverse
+  float rc2;                 // (r/h)^2 with slack: row / cell pruning is conservative, the point test decides
+  float r2_lo, r2_hi;        // fp32 screening band around r^2
+  double r2;                 // exact r^2
+  int min_neighbors;
+  int dimx, dimy, dimz;
+};
+
+// squared gap (in cells) between a point at u in [0,1) of its cell and the cell d steps away on the same axis
+__device__ __forceinline__ float gap2(int d, float u) {
+  const float g = d == 0 ? 0.f : (d > 0 ? (float)d - u : u - (float)(d + 1));
+  return g > 0.f ? g * g : 0.f;
+}
+
+template <int R, bool E16, bool U2>
+__global__ void __launch_bounds__(kFlatThreads)
+mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
+                const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
+                MmeAcc *__restrict__ acc) {
+  constexpr int SIDE = 2 * R + 1;
+  extern __shared__ __align__(16) unsigned char flat_smem[];
+  RunTab<E16> T(flat_smem);
+  const int tid = threadIdx.x;
+  const float h = C.h, r2_lo = C.r2_lo, r2_hi = C.r2_hi;
+  ThreadStats ts;
+  ts.init();
+  const long long stride = (long long)gridDim.x * kFlatThreads;
+  for (long long i = q_begin + blockIdx.x * (long long)kFlatThreads + tid; i < q_end; i += stride) {
+    const float4 qr = __ldg(rel + i);
+    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + i) + 3)));
+    const int ix = (int)qr.w;
+    const uint32_t cyz = cq / (uint32_t)C.dimx;
+    const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
+    const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
+    float gl[R], gr[R];      // squared gaps to the d-th cell on the left / right along x (increasing in d)
+#pragma unroll
+    for (int d = 1; d <= R; ++d) { gl[d - 1] = gap2(-d, ux); gr[d - 1] = gap2(d, ux); }
+    int nrun = 0;
+#pragma unroll
+    for (int dz = -R; dz <= R; ++dz) {
+      const int z = iz + dz;
+      const float remz = C.rc2 - gap2(dz, uz);
+      const float czv = (float)dz * h - qr.z;
+#pragma unroll
+      for (int dy = -R; dy <= R; ++dy) {
+        const int y = iy + dy;
+        const float rem = remz - gap2(dy, uy);
+        int da = 0, db = 0;
+#pragma unroll
+        for (int d = 0; d < R; ++d) { da -= (gl[d] <= rem) ? 1 : 0; db += (gr[d] <= rem) ? 1 : 0; }
+        const int xa = max(ix + da, 0), xb = min(ix + db, C.dimx - 1);
+        uint32_t s = 0, e = 0;
+        if ((unsigned)z < (unsigned)C.dimz && (unsigned)y < (unsigned)C.dimy && rem >= 0.f) {
+          const uint32_t row = ((uint32_t)z * (uint32_t)C.dimy + (uint32_t)y) * (uint32_t)C.dimx;
+          s = __ldg(cell_off + row + xa);
+          e = __ldg(cell_off + row + xb + 1);
+        }
+        if (e > s) { T.put(nrun, tid, s, e, dy + R, dz + R, (float)dy * h - qr.y, czv); ++nrun; }
+      }
+    }
+    Moments m;
+    m.init();
+    // one candidate: fp32 screen on the cell-relative offsets, exact fp64 decision inside the error band (rare)
+    auto process = [&](const float4 &c, float cy, float cz, uint32_t j) {
+      const float dx = fmaf(c.w - qr.w, h, c.x - qr.x), dy = c.y + cy, dz = c.z + cz;
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      if (d2 < r2_hi) {
+        bool in = true;
+        if (d2 > r2_lo) {
+          const P4 q = load_p4(S + i), p = load_p4(S + j);
+          in = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z) < C.r2;      // nanoflann RadiusResultSet: strict <
+        }
+        if (in) m.add((double)dx, (double)dy, (double)dz);
+      }
+    };
+    RunWalk w;
+    w.start(nrun);
+    if (U2) {
+      for (;;) {
+        uint32_t j0, j1;
+        float y0, z0, y1, z1;
+        if (!w.next(T, tid, h, qr.y, qr.z, R, j0, y0, z0)) break;
+        const bool v1 = w.next(T, tid, h, qr.y, qr.z, R, j1, y1, z1);
+        const float4 c0 = __ldg(rel + j0);
+        const float4 c1 = __ldg(rel + (v1 ? j1 : j0));
+        process(c0, y0, z0, j0);
+        if (v1) process(c1, y1, z1, j1);
+      }
+    } else {
+      uint32_t j0;
+      float y0, z0;
+      while (w.next(T, tid, h, qr.y, qr.z, R, j0, y0, z0)) process(__ldg(rel + j0), y0, z0, j0);
+    }
+    entropy_sorted[i] = finish_entropy(m, C.min_neighbors, ts);
+  }
+  flush_stats(ts, acc);
+}
+
+template <int R, bool E16, bool U2>
+static int launch_flat(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
+  constexpr int NROW = (2 * R + 1) * (2 * R + 1);
+  const size_t pad = getenv("ME_MME_PAD") ? (size_t)atoi(getenv("ME_MME_PAD")) : 0;   // tuning: fewer CTAs/SM, more L1
+  const size_t smem = (size_t)NROW * kFlatThreads * RunTab<E16>::kEntryBytes + pad;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  if (const char *co = getenv("ME_MME_CARVEOUT"))
+    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
+  int per_sm = 64;
+  if (const char *b = getenv("ME_MME_BLOCKS")) per_sm = std::max(1, atoi(b));
+  const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * per_sm);
+  mme_flat_kernel<R, E16, U2><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, c.d_entropy, acc);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
+template <int R>
+static int launch_flat_variant(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
+  const char *v = getenv("ME_MME_VARIANT");     // tuning switch: "<entry bytes 8|16><unroll 1|2>", e.g. "162"
+  const int code = v ? atoi(v) : 82;
+  switch (code) {
+    case 81: return launch_flat<R, false, false>(ctx, c, qb, qe, C, acc);
+    case 82: return launch_flat<R, false, true>(ctx, c, qb, qe, C, acc);
+    case 161: return launch_flat<R, true, false>(ctx, c, qb, qe, C, acc);
+    default: return launch_flat<R, true, true>(ctx, c, qb, qe, C, acc);
+  }
+}
+
 __global__ void unsort_f64_kernel(const P4 *__restrict__ S, long long n, const double *__restrict__ src,
                                   double *__restrict__ dst) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -181,10 +330,34 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   const double rc = radius / c.lat.h;
   const float rc2 = (float)(rc * rc * (1.0 + 1e-5) + 1e-4);   // row pruning is conservative; the point test decides
   if (qe > qb) {
-    const int blocks = (int)std::min<long long>((qe - qb + kThreads - 1) / kThreads, (long long)ctx->sm_count * 64);
-    mme_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, qb, qe, c.d_cell_off, c.lat, radius * radius, rc2, rings,
-                                                    min_neighbors, c.d_entropy, acc);
-    ME_LAUNCH_CHECK(ctx);
+    // the flat kernel packs run lengths into 24 bits and x indices into an fp32 mantissa
+    const bool flat = rings <= 3 && c.lat.dims[0] < (1 << 24) && (2 * rings + 1) * c.max_cell_count < (1 << 24) &&
+                      !getenv("ME_MME_WALK");
+    if (flat) {
+      MmeConst C;
+      C.h = (float)c.lat.h; C.inv_h = (float)(1.0 / c.lat.h);
+      C.rc2 = rc2;
+      C.r2 = radius * radius;
+      // fp32 screening error: |offset error| <= E per axis (cell-relative rounding 2^-24 h per operand, the fp32 value of
+      // h times <= 4 cells, one FMA rounding; plus the fp64 rounding of the cell origins), so
+      // |d2_fp32 - d2| <= 2 sqrt(3) E d + 3 E^2 + 4 * 2^-24 d2; the band is several times that at d = r
+      double maxabs = 0;
+      for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(c.bbox_min[a]), std::fabs(c.bbox_max[a])));
+      const double E = 1e-6 * c.lat.h + 4e-15 * maxabs;
+      const double band = 8.0 * radius * E + 12.0 * E * E + 1e-6 * C.r2;
+      C.r2_lo = (float)((C.r2 - band) * (1.0 - 1e-7));
+      C.r2_hi = (float)((C.r2 + band) * (1.0 + 1e-7));
+      C.min_neighbors = min_neighbors;
+      C.dimx = c.lat.dims[0]; C.dimy = c.lat.dims[1]; C.dimz = c.lat.dims[2];
+      if (rings == 1) ME_TRY(launch_flat_variant<1>(ctx, c, qb, qe, C, acc));
+      else if (rings == 2) ME_TRY(launch_flat_variant<2>(ctx, c, qb, qe, C, acc));
+      else ME_TRY(launch_flat_variant<3>(ctx, c, qb, qe, C, acc));
+    } else {
+      const int blocks = (int)std::min<long long>((qe - qb + kThreads - 1) / kThreads, (long long)ctx->sm_count * 64);
+      mme_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, qb, qe, c.d_cell_off, c.lat, radius * radius, rc2, rings,
+                                                      min_neighbors, c.d_entropy, acc);
+      ME_LAUNCH_CHECK(ctx);
+    }
   }
   MmeAcc *h = (MmeAcc *)ctx->h_pinned;
   ME_CUDA(ctx, cudaMemcpyAsync(h, acc, sizeof(MmeAcc), cudaMemcpyDeviceToHost, ctx->stream));

@@ -14,7 +14,9 @@
 // ring-expansion kernel (rare: ~0.1 % of queries on volume-filling clouds).
 #include "common.cuh"
 #include "tile.cuh"
+#include "flat.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace me {
@@ -45,6 +47,47 @@ struct LocalAcc {
 #pragma unroll
     for (int k = 0; k < 5; ++k) { n_inl[k] = 0; sum_d[k] = 0; sum_d2[k] = 0; }
   }
+  __device__ __forceinline__ void pair(double nd, double sq) { n_corr++; sum_d_all += nd; sum_d2_all += sq; }
+  __device__ __forceinline__ void inlier(int k, double nd, double sq) { sum_d[k] += nd; sum_d2[k] += sq; n_inl[k]++; }
+  __device__ __forceinline__ void nn_dist(double d) { sum_nn += d; }
+  __device__ __forceinline__ void ub() { n_ub++; }
+};
+
+// the same accumulators as a per-thread column of a shared-memory block ([field][thread], conflict-free): used by the
+// flat sweep, whose candidate loop wants the registers (the accumulators are touched once per query, not per candidate)
+struct SmemAcc {
+  static constexpr int kThreadsPerBlock = 128;
+  double *d;            // [13][threads]: sum_d[5], sum_d2[5], sum_d_all, sum_d2_all, sum_nn
+  unsigned int *u;      // [7][threads]:  n_corr, n_inl[5], n_ub
+  int tid;
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < 13; ++k) d[k * kThreadsPerBlock + tid] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) u[k * kThreadsPerBlock + tid] = 0u;
+  }
+  __device__ __forceinline__ void pair(double nd, double sq) {
+    u[tid]++; d[10 * kThreadsPerBlock + tid] += nd; d[11 * kThreadsPerBlock + tid] += sq;
+  }
+  __device__ __forceinline__ void inlier(int k, double nd, double sq) {
+    d[k * kThreadsPerBlock + tid] += nd; d[(5 + k) * kThreadsPerBlock + tid] += sq; u[(1 + k) * kThreadsPerBlock + tid]++;
+  }
+  __device__ __forceinline__ void nn_dist(double v) { d[12 * kThreadsPerBlock + tid] += v; }
+  __device__ __forceinline__ void ub() { u[6 * kThreadsPerBlock + tid]++; }
+  // block reduction + one atomic per field (call from every thread of the block)
+  __device__ void flush(AccBlock *g) {
+    __syncthreads();
+    if (tid < 13) {
+      double s = 0;
+      for (int t = 0; t < kThreadsPerBlock; ++t) s += d[tid * kThreadsPerBlock + ((t + tid) & (kThreadsPerBlock - 1))];
+      if (s != 0.0) atomicAdd(&g->sum_d[0] + tid, s);
+    } else if (tid >= 32 && tid < 39) {
+      const int k = tid - 32;
+      unsigned long long s = 0;
+      for (int t = 0; t < kThreadsPerBlock; ++t) s += u[k * kThreadsPerBlock + ((t + k) & (kThreadsPerBlock - 1))];
+      if (s) atomicAdd(&g->n_corr + k, s);   // n_corr, n_inl[5], n_ub are contiguous
+    }
+  }
 };
 
 __device__ __forceinline__ bool keep_pair(double d2, const NNConst &c) {
@@ -52,15 +95,14 @@ __device__ __forceinline__ bool keep_pair(double d2, const NNConst &c) {
 }
 
 // map_eval.cpp:1095-1123 for one kept pair (source - target)
-__device__ __forceinline__ void accum_pair(double dx, double dy, double dz, const NNConst &c, LocalAcc &a) {
+template <class Acc>
+__device__ __forceinline__ void accum_pair(double dx, double dy, double dz, const NNConst &c, Acc &a) {
   double sq = sqnorm_eigen(dx, dy, dz);
   double nd = __dsqrt_rn(sq);
-  a.n_corr++;
-  a.sum_d_all += nd;
-  a.sum_d2_all += sq;
+  a.pair(nd, sq);
 #pragma unroll
   for (int k = 0; k < 5; ++k)
-    if (nd <= c.tau[k]) { a.sum_d[k] += nd; a.sum_d2[k] += sq; a.n_inl[k]++; }
+    if (nd <= c.tau[k]) a.inlier(k, nd, sq);
 }
 
 __device__ void flush_acc(LocalAcc &a, AccBlock *g) {
@@ -146,15 +188,15 @@ __device__ __forceinline__ void search_block_global(const P4 &q, long long ix, l
 
 // after the 3x3x3 block: is the best provably the global nearest neighbour?  If so fold it into the accumulators,
 // otherwise hand the query to the ring-expansion kernel.
+template <class Acc>
 __device__ __forceinline__ void finish_query(const P4 &q, uint32_t i, long long ix, long long iy, long long iz,
                                              const Lattice &L, const NNConst &C, const Best &b,
                                              int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
                                              uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count,
-                                             LocalAcc &a) {
-  const double ux = cell_coord_cont(q.x, L, 0), uy = cell_coord_cont(q.y, L, 1), uz = cell_coord_cont(q.z, L, 2);
+                                             Acc &a, double ux, double uy, double uz, double slack_h) {
   const double g = fmin(fmin(face_dist_cells(ux, ix, 1, L.dims[0]), face_dist_cells(uy, iy, 1, L.dims[1])),
                         face_dist_cells(uz, iz, 1, L.dims[2])) * L.h;
-  const double slack = 1e-9 * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
+  const double slack = slack_h * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
   const double ge = g - slack;
   const double ge2 = ge > 0 ? ge * ge : 0.0;
   bool resolved = b.d2 < ge2;
@@ -169,7 +211,7 @@ __device__ __forceinline__ void finish_query(const P4 &q, uint32_t i, long long 
   if (beyond || !(b.d2 < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; return; }
   nn_idx[i] = b.idx;
   nn_d2[i] = b.d2;
-  if (C.want_full_cd) a.sum_nn += __dsqrt_rn(b.d2);        // map_eval.cpp:1416
+  if (C.want_full_cd) a.nn_dist(__dsqrt_rn(b.d2));        // map_eval.cpp:1416
   if (C.accumulate && keep_pair(b.d2, C)) accum_pair(b.dx, b.dy, b.dz, C, a);
 }
 
@@ -355,11 +397,134 @@ nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lat
         search_block_global(q, r0x + lx, r0y + ly, r0z + lz, R, r_off, Lr, b);
       }
       // the searched block is centred on the query's own (unclamped) reference cell; the far kernel restarts from ring 0
-      finish_query(q, pos, r0x + lx, r0y + ly, r0z + lz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a);
+      finish_query(q, pos, r0x + lx, r0y + ly, r0z + lz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a,
+                   cell_coord_cont(q.x, Lr, 0), cell_coord_cont(q.y, Lr, 1), cell_coord_cont(q.z, Lr, 2), 1e-9);
     }
     __syncthreads();   // shared tables and the staged region are re-used by the next tile
   }
   flush_acc(a, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// flat sweep.  One thread per query, queries in cell-sorted order (a warp = ~20 x-adjacent cells of one lattice row,
+// so its lanes walk the same 9 rows of the reference lattice and their loads hit the same L1 lines).  The 3x3x3 block
+// is 9 x-runs of the reference cloud; their bounds go to a per-thread run table in shared memory and the candidates
+// are walked as ONE flattened loop (lanes stay in step).  Candidates are screened in fp32 on the cell-relative copies
+// of both clouds (16 B/point; the offset between two points is rebuilt as (ix_c - ix_q) h + (rel_c - rel_q), error
+// ~1e-6 h whatever the world extent): the loop keeps the smallest and second smallest screened distance.  If the
+// runner-up is outside the fp32 error bound of the winner, only the winner is evaluated in fp64 (reference operation
+// order); otherwise every candidate inside the bound is, and ties go to the smaller caller index.
+// ---------------------------------------------------------------------------------------------------------------
+struct FlatGeom {
+  int qdimx, qdimy;            // query lattice (to decode the query's cell)
+  int rdimx, rdimy, rdimz;     // reference lattice
+  long long shx, shy, shz;     // reference cell = query cell + shift (the lattices share v and m)
+  float h;                     // cell edge
+  float eta;                   // bound on the error of the fp32 offset VECTOR
+  double inv_h;
+};
+
+template <bool E16, bool U2>
+__global__ void __launch_bounds__(kFlatThreads)
+nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
+               const P4 *__restrict__ R, const float4 *__restrict__ rrel, const uint32_t *__restrict__ r_off,
+               Lattice Lr, FlatGeom G, NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
+               uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count, AccBlock *__restrict__ acc) {
+  __shared__ __align__(16) unsigned char tab_smem[9 * kFlatThreads * RunTab<E16>::kEntryBytes];
+  __shared__ double acc_d[13 * kFlatThreads];
+  __shared__ unsigned int acc_u[7 * kFlatThreads];
+  RunTab<E16> T(tab_smem);
+  const int tid = threadIdx.x;
+  const float h = G.h;
+  SmemAcc a;
+  a.d = acc_d; a.u = acc_u; a.tid = tid;
+  a.clear();
+  const long long stride = (long long)gridDim.x * kFlatThreads;
+  for (long long i = q_begin + blockIdx.x * (long long)kFlatThreads + tid; i < q_end; i += stride) {
+    const float4 qr = __ldg(qrel + i);
+    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + i) + 3)));
+    const uint32_t cyz = cq / (uint32_t)G.qdimx;
+    // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
+    const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
+                    cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
+    const long long xa = max(cx - 1, 0ll), xb = min(cx + 1, (long long)G.rdimx - 1);
+    int nrun = 0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+      const long long z = cz + dz;
+      const float czv = (float)dz * h - qr.z;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const long long y = cy + dy;
+        uint32_t s = 0, e = 0;
+        if (z >= 0 && z < G.rdimz && y >= 0 && y < G.rdimy && xa <= xb) {
+          const uint32_t row = ((uint32_t)z * (uint32_t)G.rdimy + (uint32_t)y) * (uint32_t)G.rdimx;
+          s = __ldg(r_off + row + (uint32_t)xa);
+          e = __ldg(r_off + row + (uint32_t)xb + 1);
+        }
+        if (e > s) { T.put(nrun, tid, s, e, dy + 1, dz + 1, (float)dy * h - qr.y, czv); ++nrun; }
+      }
+    }
+    // pass 1, fp32 only: smallest and second smallest screened distance
+    const float tq = (float)cx;
+    float b1 = INFINITY, b2 = INFINITY;
+    uint32_t j1 = 0;
+    auto screen = [&](const float4 &c, float cyf, float czf) {
+      const float ddx = fmaf(c.w - tq, h, c.x - qr.x), ddy = c.y + cyf, ddz = c.z + czf;
+      return fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+    };
+    auto offer32 = [&](float d32, uint32_t j) {
+      const bool lt = d32 < b1;
+      b2 = fminf(b2, lt ? b1 : d32);
+      j1 = lt ? j : j1;
+      b1 = fminf(b1, d32);
+    };
+    RunWalk w;
+    w.start(nrun);
+    if (U2) {
+      for (;;) {
+        uint32_t j0, jn;
+        float y0, z0, y1, z1;
+        if (!w.next(T, tid, h, qr.y, qr.z, 1, j0, y0, z0)) break;
+        const bool v1 = w.next(T, tid, h, qr.y, qr.z, 1, jn, y1, z1);
+        const float4 c0 = __ldg(rrel + j0);
+        const float4 c1 = __ldg(rrel + (v1 ? jn : j0));
+        offer32(screen(c0, y0, z0), j0);
+        if (v1) offer32(screen(c1, y1, z1), jn);
+      }
+    } else {
+      uint32_t j0;
+      float y0, z0;
+      while (w.next(T, tid, h, qr.y, qr.z, 1, j0, y0, z0)) offer32(screen(__ldg(rrel + j0), y0, z0), j0);
+    }
+    const P4 q = load_p4(Q + i);
+    Best b;
+    b.init();
+    if (b1 < INFINITY) {
+      // every candidate whose true distance is <= that of j1 has d32 <= b1 + 2 E(b1), E(d2) = 2 sqrt(d2) eta + eta^2 + fp32 rounding
+      const float lim = (b1 + 3.0f * (2.f * sqrtf(b1) * G.eta + G.eta * G.eta + 1e-6f * b1)) * 1.0000005f + 1e-30f;
+      if (b2 > lim) {
+        const P4 p = load_p4(R + j1);
+        b.offer(q, p.x, p.y, p.z, orig_of(p.idx));
+      } else {
+        // near-tie (or duplicate points): settle it in fp64 with the reference's operation order
+        w.start(nrun);
+        uint32_t jj;
+        float y0, z0;
+        while (w.next(T, tid, h, qr.y, qr.z, 1, jj, y0, z0)) {
+          if (screen(__ldg(rrel + jj), y0, z0) <= lim) {
+            const P4 p = load_p4(R + jj);
+            b.offer(q, p.x, p.y, p.z, orig_of(p.idx));
+          }
+        }
+      }
+    }
+    // position inside the own cell from the cell-relative copy (error ~1e-7 cells, covered by the face-test slack)
+    finish_query(q, (uint32_t)i, cx, cy, cz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a,
+                 (double)cx + (double)qr.x * G.inv_h, (double)cy + (double)qr.y * G.inv_h,
+                 (double)cz + (double)qr.z * G.inv_h, 2e-6);
+  }
+  a.flush(acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -475,7 +640,7 @@ pair_as_written_kernel(const P4 *__restrict__ Qgt, long long n, const int32_t *_
     if (!keep_pair(nn_d2[i], C)) continue;
     const long long i_gt = orig_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Qgt + i) + 3)));
     const long long s = nn_est, t = i_gt;          // source index into gt, target index into est
-    if (s >= n_gt || t >= n_est) { a.n_ub++; continue; }
+    if (s >= n_gt || t >= n_est) { a.ub(); continue; }
     const double dx = __dsub_rn(__ldg(gt_xyz + 3 * s), __ldg(est_xyz + 3 * t));
     const double dy = __dsub_rn(__ldg(gt_xyz + 3 * s + 1), __ldg(est_xyz + 3 * t + 1));
     const double dz = __dsub_rn(__ldg(gt_xyz + 3 * s + 2), __ldg(est_xyz + 3 * t + 2));
@@ -551,12 +716,45 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     ME_CUDA(ctx, cudaFuncSetAttribute(nn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     attr_done = true;
   }
-  if (te > tb) {
-    // persistent CTAs: each walks tiles tb + blockIdx.x, + gridDim.x, ... and flushes its accumulators once
-    const unsigned grid = (unsigned)std::min<long long>(te - tb, (long long)ctx->sm_count * 16);
-    nn_tile_kernel<<<grid, kTileThreads, dyn_smem, ctx->stream>>>(
-        Qc.d_sorted, Qc.d_cell_off, Qc.lat, Qc.d_tiles, tb, te, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C, Qc.d_nn_idx,
-        Qc.d_nn_d2, far_list, far_count, acc);
+  // the flat kernel packs run lengths into 24 bits and x indices into an fp32 mantissa; otherwise the tile kernel runs
+  const bool use_tile = getenv("ME_NN_TILE") != nullptr || Qc.lat.dims[0] >= (1 << 24) || Rc.lat.dims[0] >= (1 << 24) ||
+                        3 * Rc.max_cell_count >= (1 << 24);
+  long long qb, qe;
+  shard_range(ctx, Qc.n, &qb, &qe);            // flat sweep: contiguous range of the cell-sorted query order
+  if (use_tile ? te > tb : qe > qb) {
+    if (use_tile) {
+      // persistent CTAs: each walks tiles tb + blockIdx.x, + gridDim.x, ... and flushes its accumulators once
+      const unsigned grid = (unsigned)std::min<long long>(te - tb, (long long)ctx->sm_count * 16);
+      nn_tile_kernel<<<grid, kTileThreads, dyn_smem, ctx->stream>>>(
+          Qc.d_sorted, Qc.d_cell_off, Qc.lat, Qc.d_tiles, tb, te, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C, Qc.d_nn_idx,
+          Qc.d_nn_d2, far_list, far_count, acc);
+    } else {
+      FlatGeom G;
+      G.qdimx = Qc.lat.dims[0]; G.qdimy = Qc.lat.dims[1];
+      G.rdimx = Rc.lat.dims[0]; G.rdimy = Rc.lat.dims[1]; G.rdimz = Rc.lat.dims[2];
+      G.shx = (long long)(Qc.lat.k_lo[0] - Rc.lat.k_lo[0]) * Qc.lat.m;
+      G.shy = (long long)(Qc.lat.k_lo[1] - Rc.lat.k_lo[1]) * Qc.lat.m;
+      G.shz = (long long)(Qc.lat.k_lo[2] - Rc.lat.k_lo[2]) * Qc.lat.m;
+      G.h = (float)Qc.lat.h;
+      G.inv_h = 1.0 / Qc.lat.h;
+      double maxabs = C.ref_maxabs;
+      for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(Qc.bbox_min[a]), std::fabs(Qc.bbox_max[a])));
+      // per-axis offset error <= 1e-6 h + fp64 rounding of the cell origins (see mme.cu); vector norm <= sqrt(3) times that
+      G.eta = (float)(1.7320508 * (1e-6 * Qc.lat.h + 4e-15 * maxabs));
+      const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * (getenv("ME_NN_BLOCKS") ? atoi(getenv("ME_NN_BLOCKS")) : 32));
+      const char *v = getenv("ME_NN_VARIANT");      // tuning switch: "<entry bytes 8|16><unroll 1|2>"
+      const int code = v ? atoi(v) : 81;
+#define ME_NN_FLAT_LAUNCH(E16, U2)                                                                                        \
+  nn_flat_kernel<E16, U2><<<grid, kFlatThreads, pad, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,  \
+                                                                    Rc.d_cell_off, Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,   \
+                                                                    far_list, far_count, acc)
+      const size_t pad = getenv("ME_NN_PAD") ? (size_t)atoi(getenv("ME_NN_PAD")) : 0;   // tuning: extra smem = fewer CTAs/SM, more L1
+      if (code == 81) { ME_NN_FLAT_LAUNCH(false, false); }
+      else if (code == 82) { ME_NN_FLAT_LAUNCH(false, true); }
+      else if (code == 161) { ME_NN_FLAT_LAUNCH(true, false); }
+      else { ME_NN_FLAT_LAUNCH(true, true); }
+#undef ME_NN_FLAT_LAUNCH
+    }
     ME_LAUNCH_CHECK(ctx);
     nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C,
                                                                   Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
@@ -572,17 +770,17 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       ME_LAUNCH_CHECK(ctx);
     }
   }
-  if (sharded) {
+  if (sharded && use_tile) {
     count_marked_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_nn_idx, Qc.n, n_eval);
     ME_LAUNCH_CHECK(ctx);
   }
   AccBlock *h = (AccBlock *)ctx->h_pinned;
   unsigned long long *h_eval = (unsigned long long *)((char *)ctx->h_pinned + 1024);
   ME_CUDA(ctx, cudaMemcpyAsync(h, acc, sizeof(AccBlock), cudaMemcpyDeviceToHost, ctx->stream));
-  if (sharded) ME_CUDA(ctx, cudaMemcpyAsync(h_eval, n_eval, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (sharded && use_tile) ME_CUDA(ctx, cudaMemcpyAsync(h_eval, n_eval, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::memset(out, 0, sizeof(*out));
-  out->n_query = sharded ? (int64_t)*h_eval : Qc.n;
+  out->n_query = !sharded ? Qc.n : (use_tile ? (int64_t)*h_eval : qe - qb);
   out->n_corr = (int64_t)h->n_corr;
   for (int k = 0; k < 5; ++k) { out->n_inlier[k] = (int64_t)h->n_inl[k]; out->sum_d[k] = h->sum_d[k]; out->sum_d2[k] = h->sum_d2[k]; }
   out->n_ub = (int64_t)h->n_ub;
