@@ -57,6 +57,7 @@ static void free_cloud(Cloud &c) {
   if (c.d_cell_id) cudaFree(c.d_cell_id);
   if (c.d_nn_idx) cudaFree(c.d_nn_idx);
   if (c.d_nn_d2) cudaFree(c.d_nn_d2);
+  if (c.d_nn_sq) cudaFree(c.d_nn_sq);
   if (c.d_entropy) cudaFree(c.d_entropy);
   if (c.d_tiles) cudaFree(c.d_tiles);
   if (c.upload_done) cudaEventDestroy(c.upload_done);

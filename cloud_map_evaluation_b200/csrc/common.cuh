@@ -61,8 +61,9 @@ struct Cloud {
   bool upload_pending = false;
   // per-query results, SORTED order of this cloud (unsorted on demand)
   int32_t *d_nn_idx = nullptr;      // nearest neighbour in the other cloud (caller index there)
-  double *d_nn_d2 = nullptr;
-  long long cap_nn = 0, cap_nn_d2 = 0;
+  double *d_nn_d2 = nullptr;        // squared distance as nanoflann accumulates it (cut-off tests, full Chamfer)
+  double *d_nn_sq = nullptr;        // squared norm as Eigen accumulates it (inlier statistics)
+  long long cap_nn = 0, cap_nn_d2 = 0, cap_nn_sq = 0;
   bool nn_valid = false;
   double *d_entropy = nullptr;
   long long cap_entropy = 0;

@@ -53,56 +53,24 @@ struct LocalAcc {
   __device__ __forceinline__ void ub() { n_ub++; }
 };
 
-// the same accumulators as a per-thread column of a shared-memory block ([field][thread], conflict-free): used by the
-// flat sweep, whose candidate loop wants the registers (the accumulators are touched once per query, not per candidate)
-struct SmemAcc {
-  static constexpr int kThreadsPerBlock = 128;
-  double *d;            // [13][threads]: sum_d[5], sum_d2[5], sum_d_all, sum_d2_all, sum_nn
-  unsigned int *u;      // [7][threads]:  n_corr, n_inl[5], n_ub
-  int tid;
-  __device__ __forceinline__ void clear() {
-#pragma unroll
-    for (int k = 0; k < 13; ++k) d[k * kThreadsPerBlock + tid] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) u[k * kThreadsPerBlock + tid] = 0u;
-  }
-  __device__ __forceinline__ void pair(double nd, double sq) {
-    u[tid]++; d[10 * kThreadsPerBlock + tid] += nd; d[11 * kThreadsPerBlock + tid] += sq;
-  }
-  __device__ __forceinline__ void inlier(int k, double nd, double sq) {
-    d[k * kThreadsPerBlock + tid] += nd; d[(5 + k) * kThreadsPerBlock + tid] += sq; u[(1 + k) * kThreadsPerBlock + tid]++;
-  }
-  __device__ __forceinline__ void nn_dist(double v) { d[12 * kThreadsPerBlock + tid] += v; }
-  __device__ __forceinline__ void ub() { u[6 * kThreadsPerBlock + tid]++; }
-  // block reduction + one atomic per field (call from every thread of the block)
-  __device__ void flush(AccBlock *g) {
-    __syncthreads();
-    if (tid < 13) {
-      double s = 0;
-      for (int t = 0; t < kThreadsPerBlock; ++t) s += d[tid * kThreadsPerBlock + ((t + tid) & (kThreadsPerBlock - 1))];
-      if (s != 0.0) atomicAdd(&g->sum_d[0] + tid, s);
-    } else if (tid >= 32 && tid < 39) {
-      const int k = tid - 32;
-      unsigned long long s = 0;
-      for (int t = 0; t < kThreadsPerBlock; ++t) s += u[k * kThreadsPerBlock + ((t + k) & (kThreadsPerBlock - 1))];
-      if (s) atomicAdd(&g->n_corr + k, s);   // n_corr, n_inl[5], n_ub are contiguous
-    }
-  }
-};
 
 __device__ __forceinline__ bool keep_pair(double d2, const NNConst &c) {
   return c.cutoff_mode == ME_CUTOFF_SQDIST_LE_R ? (d2 <= c.cutoff) : (d2 < c.cutoff);
 }
 
 // map_eval.cpp:1095-1123 for one kept pair (source - target)
+// sq = Eigen's squaredNorm of (source - target), x*x + (y*y + z*z)
 template <class Acc>
-__device__ __forceinline__ void accum_pair(double dx, double dy, double dz, const NNConst &c, Acc &a) {
-  double sq = sqnorm_eigen(dx, dy, dz);
+__device__ __forceinline__ void accum_sq(double sq, const NNConst &c, Acc &a) {
   double nd = __dsqrt_rn(sq);
   a.pair(nd, sq);
 #pragma unroll
   for (int k = 0; k < 5; ++k)
     if (nd <= c.tau[k]) a.inlier(k, nd, sq);
+}
+template <class Acc>
+__device__ __forceinline__ void accum_pair(double dx, double dy, double dz, const NNConst &c, Acc &a) {
+  accum_sq(sqnorm_eigen(dx, dy, dz), c, a);
 }
 
 __device__ void flush_acc(LocalAcc &a, AccBlock *g) {
@@ -186,14 +154,15 @@ __device__ __forceinline__ void search_block_global(const P4 &q, long long ix, l
   }
 }
 
-// after the 3x3x3 block: is the best provably the global nearest neighbour?  If so fold it into the accumulators,
-// otherwise hand the query to the ring-expansion kernel.
-template <class Acc>
+// after the 3x3x3 block: is the best provably the global nearest neighbour?  If so record it (index, nanoflann-order d2 for
+// the cut-off, Eigen-order squared norm for the statistics; nn_stats_kernel folds them into the accumulators), otherwise
+// hand the query to the ring-expansion kernel.
 __device__ __forceinline__ void finish_query(const P4 &q, uint32_t i, long long ix, long long iy, long long iz,
                                              const Lattice &L, const NNConst &C, const Best &b,
                                              int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
-                                             uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count,
-                                             Acc &a, double ux, double uy, double uz, double slack_h) {
+                                             double *__restrict__ nn_sq, uint32_t *__restrict__ far_list,
+                                             unsigned int *__restrict__ far_count, double ux, double uy, double uz,
+                                             double slack_h) {
   const double g = fmin(fmin(face_dist_cells(ux, ix, 1, L.dims[0]), face_dist_cells(uy, iy, 1, L.dims[1])),
                         face_dist_cells(uz, iz, 1, L.dims[2])) * L.h;
   const double slack = slack_h * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
@@ -211,8 +180,7 @@ __device__ __forceinline__ void finish_query(const P4 &q, uint32_t i, long long 
   if (beyond || !(b.d2 < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; return; }
   nn_idx[i] = b.idx;
   nn_d2[i] = b.d2;
-  if (C.want_full_cd) a.nn_dist(__dsqrt_rn(b.d2));        // map_eval.cpp:1416
-  if (C.accumulate && keep_pair(b.d2, C)) accum_pair(b.dx, b.dy, b.dz, C, a);
+  nn_sq[i] = sqnorm_eigen(b.dx, b.dy, b.dz);
 }
 
 // clamp a (possibly far outside) lattice coordinate to one cell beyond the lattice
@@ -235,8 +203,8 @@ __global__ void __launch_bounds__(kTileThreads)
 nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lattice Lq,
                const uint32_t *__restrict__ tiles, long long t_begin, long long t_end, const P4 *__restrict__ R,
                const uint32_t *__restrict__ r_off, Lattice Lr, NNConst C, int32_t *__restrict__ nn_idx,
-               double *__restrict__ nn_d2, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count,
-               AccBlock *__restrict__ acc) {
+               double *__restrict__ nn_d2, double *__restrict__ nn_sq, uint32_t *__restrict__ far_list,
+               unsigned int *__restrict__ far_count) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P4 *raw = reinterpret_cast<P4 *>(smem_raw);
   float4 *rel = reinterpret_cast<float4 *>(smem_raw + (size_t)kNNCap * sizeof(P4));
@@ -256,8 +224,6 @@ nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lat
   const float eta = (float)(7.0 * 3.5 * Lq.h * 5.9604645e-8);
   if (tid == 0) mbar_init(&mbar, 1);
   uint32_t phase = 0;
-  LocalAcc a;
-  a.clear();
 
   for (long long t = t_begin + blockIdx.x; t < t_end; t += gridDim.x) {
     const uint32_t tile = tiles[t];
@@ -397,12 +363,11 @@ nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lat
         search_block_global(q, r0x + lx, r0y + ly, r0z + lz, R, r_off, Lr, b);
       }
       // the searched block is centred on the query's own (unclamped) reference cell; the far kernel restarts from ring 0
-      finish_query(q, pos, r0x + lx, r0y + ly, r0z + lz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a,
+      finish_query(q, pos, r0x + lx, r0y + ly, r0z + lz, Lr, C, b, nn_idx, nn_d2, nn_sq, far_list, far_count,
                    cell_coord_cont(q.x, Lr, 0), cell_coord_cont(q.y, Lr, 1), cell_coord_cont(q.z, Lr, 2), 1e-9);
     }
     __syncthreads();   // shared tables and the staged region are re-used by the next tile
   }
-  flush_acc(a, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -429,16 +394,11 @@ __global__ void __launch_bounds__(kFlatThreads)
 nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
                const P4 *__restrict__ R, const float4 *__restrict__ rrel, const uint32_t *__restrict__ r_off,
                Lattice Lr, FlatGeom G, NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
-               uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count, AccBlock *__restrict__ acc) {
+               double *__restrict__ nn_sq, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count) {
   __shared__ __align__(16) unsigned char tab_smem[9 * kFlatThreads * RunTab<E16>::kEntryBytes];
-  __shared__ double acc_d[13 * kFlatThreads];
-  __shared__ unsigned int acc_u[7 * kFlatThreads];
   RunTab<E16> T(tab_smem);
   const int tid = threadIdx.x;
   const float h = G.h;
-  SmemAcc a;
-  a.d = acc_d; a.u = acc_u; a.tid = tid;
-  a.clear();
   const long long stride = (long long)gridDim.x * kFlatThreads;
   for (long long i = q_begin + blockIdx.x * (long long)kFlatThreads + tid; i < q_end; i += stride) {
     const float4 qr = __ldg(qrel + i);
@@ -520,11 +480,10 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
       }
     }
     // position inside the own cell from the cell-relative copy (error ~1e-7 cells, covered by the face-test slack)
-    finish_query(q, (uint32_t)i, cx, cy, cz, Lr, C, b, nn_idx, nn_d2, far_list, far_count, a,
+    finish_query(q, (uint32_t)i, cx, cy, cz, Lr, C, b, nn_idx, nn_d2, nn_sq, far_list, far_count,
                  (double)cx + (double)qr.x * G.inv_h, (double)cy + (double)qr.y * G.inv_h,
                  (double)cz + (double)qr.z * G.inv_h, 2e-6);
   }
-  a.flush(acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -593,32 +552,41 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, const uint32_t
       if (beyond || !(best < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; }
       else {
         nn_idx[i] = bidx;
-        nn_d2[i] = best;
-        if (C.want_full_cd) atomicAdd(&acc->sum_nn, __dsqrt_rn(best));
-        // pair statistics of far queries: nn_far_accum_kernel (needs the winner's coordinates)
+        nn_d2[i] = best;      // the Eigen-order squared norm follows in nn_far_sq_kernel (needs the winner's coordinates)
       }
     }
   }
 }
 
-// far queries' pair statistics (the winner's coordinates come from the caller-order reference array)
+// far queries: Eigen-order squared norm of (query - winner); the winner's coordinates come from the caller-order array
 __global__ void __launch_bounds__(kThreads)
-nn_far_accum_kernel(const P4 *__restrict__ Q, const double *__restrict__ ref_xyz, NNConst C,
-                    const int32_t *__restrict__ nn_idx, const double *__restrict__ nn_d2,
-                    const uint32_t *__restrict__ far_list, const unsigned int *__restrict__ far_count,
-                    AccBlock *__restrict__ acc) {
-  LocalAcc a;
-  a.clear();
+nn_far_sq_kernel(const P4 *__restrict__ Q, const double *__restrict__ ref_xyz, const int32_t *__restrict__ nn_idx,
+                 double *__restrict__ nn_sq, const uint32_t *__restrict__ far_list,
+                 const unsigned int *__restrict__ far_count) {
   const unsigned int nfar = *far_count;
   for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < nfar; w += (long long)gridDim.x * blockDim.x) {
     const long long i = far_list[w];
     const int32_t j = nn_idx[i];
     if (j < 0) continue;
-    const double d2 = nn_d2[i];
-    if (!keep_pair(d2, C)) continue;
     const P4 q = load_p4(Q + i);
     const double px = __ldg(ref_xyz + 3ll * j), py = __ldg(ref_xyz + 3ll * j + 1), pz = __ldg(ref_xyz + 3ll * j + 2);
-    accum_pair(__dsub_rn(q.x, px), __dsub_rn(q.y, py), __dsub_rn(q.z, pz), C, a);
+    nn_sq[i] = sqnorm_eigen(__dsub_rn(q.x, px), __dsub_rn(q.y, py), __dsub_rn(q.z, pz));
+  }
+}
+
+// streaming pass over the per-query results of a sweep: the five-threshold accumulators (map_eval.cpp:1095-1123) and the
+// full-Chamfer sum (:1416).  Entries < 0 are queries without a neighbour within reach (-1) or owned by another rank (-2).
+__global__ void __launch_bounds__(kThreads)
+nn_stats_kernel(long long i_begin, long long i_end, const int32_t *__restrict__ nn_idx, const double *__restrict__ nn_d2,
+                const double *__restrict__ nn_sq, NNConst C, AccBlock *__restrict__ acc) {
+  LocalAcc a;
+  a.clear();
+  for (long long i = i_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < i_end;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (__ldg(nn_idx + i) < 0) continue;
+    const double d2 = __ldg(nn_d2 + i);
+    if (C.want_full_cd) a.nn_dist(__dsqrt_rn(d2));
+    if (C.accumulate && keep_pair(d2, C)) accum_sq(__ldg(nn_sq + i), C, a);
   }
   flush_acc(a, acc);
 }
@@ -696,6 +664,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
 
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_idx, &Qc.cap_nn, Qc.n, sizeof(int32_t)));
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_d2, &Qc.cap_nn_d2, Qc.n, sizeof(double)));
+  ME_TRY(ensure(ctx, (void **)&Qc.d_nn_sq, &Qc.cap_nn_sq, Qc.n, sizeof(double)));
   // work buffer: far list (n uint32) after a 256-byte header holding the far counter and the query counter
   ME_TRY(ensure_work(ctx, 256 + (size_t)Qc.n * sizeof(uint32_t)));
   unsigned int *far_count = (unsigned int *)ctx->d_work;
@@ -727,7 +696,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       const unsigned grid = (unsigned)std::min<long long>(te - tb, (long long)ctx->sm_count * 16);
       nn_tile_kernel<<<grid, kTileThreads, dyn_smem, ctx->stream>>>(
           Qc.d_sorted, Qc.d_cell_off, Qc.lat, Qc.d_tiles, tb, te, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C, Qc.d_nn_idx,
-          Qc.d_nn_d2, far_list, far_count, acc);
+          Qc.d_nn_d2, Qc.d_nn_sq, far_list, far_count);
     } else {
       FlatGeom G;
       G.qdimx = Qc.lat.dims[0]; G.qdimy = Qc.lat.dims[1];
@@ -743,11 +712,11 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       G.eta = (float)(1.7320508 * (1e-6 * Qc.lat.h + 4e-15 * maxabs));
       const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * (getenv("ME_NN_BLOCKS") ? atoi(getenv("ME_NN_BLOCKS")) : 32));
       const char *v = getenv("ME_NN_VARIANT");      // tuning switch: "<entry bytes 8|16><unroll 1|2>"
-      const int code = v ? atoi(v) : 81;
+      const int code = v ? atoi(v) : 161;
 #define ME_NN_FLAT_LAUNCH(E16, U2)                                                                                        \
   nn_flat_kernel<E16, U2><<<grid, kFlatThreads, pad, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,  \
                                                                     Rc.d_cell_off, Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,   \
-                                                                    far_list, far_count, acc)
+                                                                    Qc.d_nn_sq, far_list, far_count)
       const size_t pad = getenv("ME_NN_PAD") ? (size_t)atoi(getenv("ME_NN_PAD")) : 0;   // tuning: extra smem = fewer CTAs/SM, more L1
       if (code == 81) { ME_NN_FLAT_LAUNCH(false, false); }
       else if (code == 82) { ME_NN_FLAT_LAUNCH(false, true); }
@@ -760,8 +729,14 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
                                                                   Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
     ME_LAUNCH_CHECK(ctx);
     if (C.accumulate) {
-      nn_far_accum_kernel<<<ctx->sm_count, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_xyz, C, Qc.d_nn_idx, Qc.d_nn_d2,
-                                                                       far_list, far_count, acc);
+      nn_far_sq_kernel<<<ctx->sm_count, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_xyz, Qc.d_nn_idx, Qc.d_nn_sq, far_list,
+                                                                    far_count);
+      ME_LAUNCH_CHECK(ctx);
+    }
+    if (C.accumulate || C.want_full_cd) {
+      const long long sb = use_tile ? 0 : qb, se = use_tile ? Qc.n : qe;
+      const int sblocks = (int)std::min<long long>((se - sb + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
+      nn_stats_kernel<<<std::max(1, sblocks), kThreads, 0, ctx->stream>>>(sb, se, Qc.d_nn_idx, Qc.d_nn_d2, Qc.d_nn_sq, C, acc);
       ME_LAUNCH_CHECK(ctx);
     }
     if (as_written) {
