@@ -253,7 +253,7 @@ def main():
         value = n_est / (ms_dev * 1e-3) / 1e6
         e2e = n_est / (ms_e2e * 1e-3) / 1e6
         peak, peak_src = _peaks()
-        # dominant kernel: the MME radius sweep of the estimated map (stage "mme_est" = mme_kernel + a 1-thread init).
+        # dominant kernel: the MME radius sweep of the estimated map (stage "mme_est" = mme_flat_kernel + a 1-thread init).
         # algorithmic bytes per launch: 12 B query + 12 B reference + 8 B entropy out per point of this
         # rank's query range
         nq = n_est * (rank + 1) // world - n_est * rank // world
@@ -262,12 +262,13 @@ def main():
         dom_ms = stage_ms.get(dom, 0.0)
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
         traffic = _profile_traffic()
-        roofline = {"bound": "hbm", "kernel": "mme_kernel" if cfg["mme"] else "nn_sweep_kernel",
+        roofline = {"bound": "hbm", "kernel": "mme_flat_kernel" if cfg["mme"] else "nn_flat_kernel",
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
                     "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                    "note": "issue/FP64-bound neighbour sweep; the HBM fraction is small by construction (SURVEY §8d)"}
+                    "note": "neighbour sweep bound by issue slots and L1/L2 latency (~137 candidate tests per query served "
+                            "from cache); the HBM fraction is small by construction (SURVEY §8d, DESIGN §3)"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O

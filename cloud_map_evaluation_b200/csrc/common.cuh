@@ -56,6 +56,7 @@ struct Cloud {
   uint32_t *d_tiles = nullptr;      // non-empty query tiles (tile id = (bz*nb[1]+by)*nb[0]+bx)
   long long cap_tiles = 0;
   long long n_tiles = 0;
+  bool tiles_valid = false;
   long long max_cell_count = 0;     // points in the fullest cell
   cudaEvent_t upload_done = nullptr;  // recorded on the copy stream after me_set_cloud's H2D
   bool upload_pending = false;
@@ -144,6 +145,7 @@ int wait_upload(me_ctx *ctx, int which);
 int compute_bbox(me_ctx *ctx, int which);
 int build_grid(me_ctx *ctx, int which);
 int build_both(me_ctx *ctx);
+int build_tiles(me_ctx *ctx, int which);
 int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e);
 int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2);
 int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out);

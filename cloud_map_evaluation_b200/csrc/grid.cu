@@ -26,19 +26,42 @@ __global__ void bbox_init_kernel(unsigned long long *s) {
   else if (t == 6) s[t] = 0ull;
 }
 
-__global__ void __launch_bounds__(kThreads) bbox_kernel(const double *__restrict__ xyz, long long n,
+__global__ void __launch_bounds__(kThreads) bbox_kernel(const double *__restrict__ xyz, long long n, int lead,
                                                         unsigned long long *__restrict__ s) {
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   unsigned long long bad = 0;
-  long long total = 3 * n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    double v = __ldg(xyz + i);
-    int a = (int)(i % 3);
-    if (!isfinite(v)) { bad++; continue; }
+  // the coordinates as 16-byte pairs (after `lead` = 0 or 1 leading scalars that make the rest 16-byte aligned):
+  // thread t of a pass reads pair t = coordinates lead + 2t, lead + 2t + 1; the stride of a pass is a multiple of 3
+  // pairs, so a thread always sees the same two axes
+  const long long ncoord = 3 * n - lead, npairs = ncoord / 2;
+  const long long stride = ((long long)gridDim.x * blockDim.x / 3) * 3;
+  const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int a0 = (int)((lead + 2 * t0) % 3), a1 = (a0 + 1) % 3;
+  double lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
+  if (t0 < stride) {
+    const double2 *pairs = reinterpret_cast<const double2 *>(xyz + lead);
+    for (long long t = t0; t < npairs; t += stride) {
+      const double2 v = __ldg(pairs + t);
+      if (isfinite(v.x)) { lo0 = fmin(lo0, v.x); hi0 = fmax(hi0, v.x); } else bad++;
+      if (isfinite(v.y)) { lo1 = fmin(lo1, v.y); hi1 = fmax(hi1, v.y); } else bad++;
+    }
+  }
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-      if (a == k) { mn[k] = fmin(mn[k], v); mx[k] = fmax(mx[k], v); }
+  for (int k = 0; k < 3; ++k) {
+    if (a0 == k) { mn[k] = fmin(mn[k], lo0); mx[k] = fmax(mx[k], hi0); }
+    if (a1 == k) { mn[k] = fmin(mn[k], lo1); mx[k] = fmax(mx[k], hi1); }
+  }
+  if (t0 == 0) {      // the scalars the pairs do not cover: the leading one (x of point 0) and, if odd, the last one
+    for (int e = 0; e < 2; ++e) {
+      const long long ci = e == 0 ? 0 : lead + 2 * npairs;
+      if ((e == 0 && lead == 0) || ci >= 3 * n) continue;
+      const double v = __ldg(xyz + ci);
+      const int k = (int)(ci % 3);
+      if (isfinite(v)) {
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) if (kk == k) { mn[kk] = fmin(mn[kk], v); mx[kk] = fmax(mx[kk], v); }
+      } else bad++;
+    }
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
@@ -73,8 +96,9 @@ int compute_bbox(me_ctx *ctx, int which) {
   unsigned long long *s = (unsigned long long *)ctx->d_scratch;
   bbox_init_kernel<<<1, 32, 0, ctx->stream>>>(s);
   ME_LAUNCH_CHECK(ctx);
-  int blocks = (int)std::min<long long>((3 * c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-  bbox_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, s);
+  int blocks = (int)std::min<long long>((3 * c.n / 2 + kThreads - 1) / kThreads + 1, (long long)ctx->sm_count * 16);
+  const int lead = (int)(((uintptr_t)c.d_xyz >> 3) & 1);     // 8- but not 16-byte aligned device buffers
+  bbox_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, lead, s);
   ME_LAUNCH_CHECK(ctx);
   unsigned long long *h = (unsigned long long *)ctx->h_pinned;
   ME_CUDA(ctx, cudaMemcpyAsync(h, s, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -233,14 +257,15 @@ __global__ void __launch_bounds__(kThreads) rel_kernel(const P4 *__restrict__ so
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// query tiles: every kTileEdge^3 block of cells that holds at least one point (from the histogram, before the scan)
+// query tiles (tile sweep only, built on demand): every kTileEdge^3 block of cells that holds at least one point
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) tile_list_kernel(const uint32_t *__restrict__ count, Lattice L,
+__global__ void __launch_bounds__(kThreads) tile_list_kernel(const uint32_t *__restrict__ off, Lattice L,
                                                              uint32_t *__restrict__ tiles,
                                                              unsigned long long *__restrict__ n_tiles) {
   const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nt; t += (long long)gridDim.x * blockDim.x) {
     const int bx = (int)(t % L.nb[0]), by = (int)((t / L.nb[0]) % L.nb[1]), bz = (int)(t / ((long long)L.nb[0] * L.nb[1]));
+    const int xa = bx * kTileEdge, xb = min(xa + kTileEdge, L.dims[0]);
     uint32_t tot = 0;
     for (int dz = 0; dz < kTileEdge; ++dz) {
       const int z = bz * kTileEdge + dz;
@@ -248,12 +273,31 @@ __global__ void __launch_bounds__(kThreads) tile_list_kernel(const uint32_t *__r
       for (int dy = 0; dy < kTileEdge; ++dy) {
         const int y = by * kTileEdge + dy;
         if (y >= L.dims[1]) break;
-        const long long row = ((long long)z * L.dims[1] + y) * L.dims[0] + (long long)bx * kTileEdge;
-        for (int dx = 0; dx < kTileEdge && bx * kTileEdge + dx < L.dims[0]; ++dx) tot += __ldg(count + row + dx);
+        const long long row = ((long long)z * L.dims[1] + y) * L.dims[0];
+        tot += __ldg(off + row + xb) - __ldg(off + row + xa);
       }
     }
     if (tot) tiles[atomicAdd(n_tiles, 1ull)] = (uint32_t)t;
   }
+}
+
+int build_tiles(me_ctx *ctx, int which) {
+  Cloud &c = ctx->cloud[which];
+  if (c.tiles_valid) return ME_OK;
+  const Lattice &L = c.lat;
+  const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
+  ME_TRY(ensure(ctx, (void **)&c.d_tiles, &c.cap_tiles, std::min<long long>(nt, c.n), sizeof(uint32_t)));
+  unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
+  ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), ctx->stream));
+  const int blocks = (int)std::min<long long>((nt + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  tile_list_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off, L, c.d_tiles, d_nt);
+  ME_LAUNCH_CHECK(ctx);
+  unsigned long long *h_nt = (unsigned long long *)ctx->h_pinned + 8;
+  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  c.n_tiles = (long long)h_nt[0];
+  c.tiles_valid = true;
+  return ME_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -391,17 +435,11 @@ int build_grid(me_ctx *ctx, int which) {
   (void)planned_here;
   c.lat = L;
 
-  // non-empty query tiles, from the histogram
-  const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
-  ME_TRY(ensure(ctx, (void **)&c.d_tiles, &c.cap_tiles, std::min<long long>(nt, c.n), sizeof(uint32_t)));
-  // scratch slots: [8] number of tiles, [9] occupied cells, [10] largest cell (bounds the run lengths of the sweeps)
+  // scratch slots: [9] occupied cells, [10] largest cell (bounds the run lengths of the sweeps)
   unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
   ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, 3 * sizeof(unsigned long long), ctx->stream));
   {
-    int blocks = (int)std::min<long long>((nt + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-    tile_list_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L, c.d_tiles, d_nt);
-    ME_LAUNCH_CHECK(ctx);
-    blocks = (int)std::min<long long>((L.ncells + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+    const int blocks = (int)std::min<long long>((L.ncells + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
     occupancy_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, d_nt + 1);
     ME_LAUNCH_CHECK(ctx);
   }
@@ -427,8 +465,8 @@ int build_grid(me_ctx *ctx, int which) {
   rel_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.n, L, c.d_rel);
   ME_LAUNCH_CHECK(ctx);
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  c.n_tiles = (long long)h_nt[0];
   c.max_cell_count = (long long)h_nt[2];
+  c.tiles_valid = false;
   c.grid_valid = true;
   c.nn_valid = false;
   c.entropy_valid = false;

@@ -648,8 +648,6 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   Cloud &Qc = ctx->cloud[qwhich];
   Cloud &Rc = ctx->cloud[1 - qwhich];
   StageTimer timer(ctx, stage);
-  long long tb, te;
-  shard_range(ctx, Qc.n_tiles, &tb, &te);      // query tiles are sharded across ranks
 
   NNConst C;
   for (int k = 0; k < 5; ++k) C.tau[k] = p->tau[k];
@@ -688,8 +686,12 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   // the flat kernel packs run lengths into 24 bits and x indices into an fp32 mantissa; otherwise the tile kernel runs
   const bool use_tile = getenv("ME_NN_TILE") != nullptr || Qc.lat.dims[0] >= (1 << 24) || Rc.lat.dims[0] >= (1 << 24) ||
                         3 * Rc.max_cell_count >= (1 << 24);
-  long long qb, qe;
+  long long qb, qe, tb = 0, te = 0;
   shard_range(ctx, Qc.n, &qb, &qe);            // flat sweep: contiguous range of the cell-sorted query order
+  if (use_tile) {
+    ME_TRY(build_tiles(ctx, qwhich));
+    shard_range(ctx, Qc.n_tiles, &tb, &te);    // tile sweep: query tiles are sharded across ranks
+  }
   if (use_tile ? te > tb : qe > qb) {
     if (use_tile) {
       // persistent CTAs: each walks tiles tb + blockIdx.x, + gridDim.x, ... and flushes its accumulators once

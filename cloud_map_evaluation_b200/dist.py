@@ -47,23 +47,25 @@ def unpack(ints, flts, mins, maxs, nn_e, nn_g, mme_list):
 
 
 def allreduce_accumulators(nn_e, nn_g, mme_list, device=None, group=None):
-    """In-place all-reduce of the partial accumulators of every rank.  Integer counts are order-independent, so the
-    reduced inlier counts are bit-exact for any world size; fp64 sums differ from the 1-GPU run by rounding only."""
+    """In-place all-reduce of the partial accumulators of every rank: ONE SUM all-reduce over the whole block (the
+    integer counts ride along as fp64 — they stay below 2^53, so their sum is exact and order-independent: the reduced
+    inlier counts are bit-exact for any world size; fp64 sums differ from the 1-GPU run by rounding only), plus one MAX
+    all-reduce over [max entropy, -min entropy] when MME was evaluated (map_eval.cpp:697-701)."""
     import torch
     import torch.distributed as dist
     ints, flts, mins, maxs = pack(nn_e, nn_g, mme_list)
-    ti = torch.tensor(ints, dtype=torch.int64, device=device)
-    tf = torch.tensor(flts, dtype=torch.float64, device=device)
-    dist.all_reduce(ti, group=group)
-    dist.all_reduce(tf, group=group)
-    tmin = tmax = None
+    assert all(abs(v) < 2 ** 53 for v in ints)
+    t = torch.tensor([float(v) for v in ints] + flts, dtype=torch.float64, device=device)
+    dist.all_reduce(t, group=group)
+    out = t.cpu().tolist()
+    ri, rf = [int(round(v)) for v in out[:len(ints)]], out[len(ints):]
+    rmin, rmax = [], []
     if mins:
-        tmin = torch.tensor(mins, dtype=torch.float64, device=device)
-        tmax = torch.tensor(maxs, dtype=torch.float64, device=device)
-        dist.all_reduce(tmin, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX, group=group)
-    unpack(ti.cpu().tolist(), tf.cpu().tolist(), tmin.cpu().tolist() if mins else [], tmax.cpu().tolist() if mins else [],
-           nn_e, nn_g, mme_list)
+        tx = torch.tensor(list(maxs) + [-v for v in mins], dtype=torch.float64, device=device)
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX, group=group)
+        ox = tx.cpu().tolist()
+        rmax, rmin = ox[:len(maxs)], [-v for v in ox[len(maxs):]]
+    unpack(ri, rf, rmin, rmax, nn_e, nn_g, mme_list)
 
 
 def shard_range(n, rank, world):

@@ -324,3 +324,26 @@ def test_device_resident_cloud_and_errors(api):
         with pytest.raises(api.MapEvalError):
             ctx.calculateMetricsWithInitialMatrix(p)             # non-finite coordinates are rejected
         assert ctx.launch_count() > 0
+
+
+@pytest.mark.parametrize("n_est", [5001, 5002])
+def test_unaligned_device_buffer_and_extreme_points(api, O, n_est):
+    """Device buffers that are 8- but not 16-byte aligned, odd/even coordinate counts, and the extreme coordinates placed
+    on the first and last scalars (the bbox reduction reads 16-byte pairs plus the leftover scalars)."""
+    import torch
+    est, gt, cfg = synth.make_pair("C1", scale=0.06)
+    est = est[:n_est].copy()
+    est[0, 0] = -3.5          # global min x on the leading scalar
+    est[-1, 2] = 7.25         # global max z on the trailing scalar
+    p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+    exp = O.eval_nn(est, gt, p)
+    buf = torch.zeros(3 * n_est + 1, dtype=torch.float64, device="cuda")
+    buf[1:] = torch.from_numpy(est.reshape(-1)).cuda()
+    view = buf[1:]
+    assert view.data_ptr() % 16 == 8
+    tg = torch.from_numpy(gt).cuda()
+    with api.MapEvalB200(stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        ctx.set_cloud_device(A.ME_CLOUD_EST, view.data_ptr(), n_est, keepalive=buf)
+        ctx.set_cloud_device(A.ME_CLOUD_GT, tg.data_ptr(), len(gt), keepalive=tg)
+        got = ctx.calculateMetricsWithInitialMatrix(p)
+    _cmp_nn(got, exp)
