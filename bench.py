@@ -160,6 +160,12 @@ def main():
         run_reference(args)
         return
 
+    # exactly ONE line may reach stdout (the JSON record): libraries that print there (NCCL's version banner) are sent
+    # to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from cloud_map_evaluation_b200 import api
@@ -302,7 +308,7 @@ def main():
                       "awd": results["awd"].awd if results["awd"] else None,
                       "scs": results["awd"].scs if results["awd"] else None, "n_far": list(results["n_far"])},
         }
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -60,6 +60,7 @@ static void free_cloud(Cloud &c) {
   if (c.d_nn_sq) cudaFree(c.d_nn_sq);
   if (c.d_entropy) cudaFree(c.d_entropy);
   if (c.d_tiles) cudaFree(c.d_tiles);
+  if (c.d_tile_pos) cudaFree(c.d_tile_pos);
   if (c.upload_done) cudaEventDestroy(c.upload_done);
   c = Cloud();
 }
@@ -161,6 +162,7 @@ int me_set_shard(me_ctx *ctx, int32_t rank, int32_t world) {
   ctx->rank = rank; ctx->world = world;
   ctx->cloud[0].nn_valid = ctx->cloud[1].nn_valid = false;
   ctx->cloud[0].entropy_valid = ctx->cloud[1].entropy_valid = false;
+  ctx->cloud[0].shard_valid = ctx->cloud[1].shard_valid = false;
   return ME_OK;
 }
 

@@ -57,6 +57,11 @@ struct Cloud {
   long long cap_tiles = 0;
   long long n_tiles = 0;
   bool tiles_valid = false;
+  uint32_t *d_tile_pos = nullptr;   // tile-list build scratch (flags -> positions)
+  long long cap_tile_pos = 0;
+  long long shard_b = 0, shard_e = 0;   // this rank's cell-aligned query range (query_shard)
+  int shard_rank = -1, shard_world = 0;
+  bool shard_valid = false;
   long long max_cell_count = 0;     // points in the fullest cell
   cudaEvent_t upload_done = nullptr;  // recorded on the copy stream after me_set_cloud's H2D
   bool upload_pending = false;
@@ -128,7 +133,8 @@ int ensure_work(me_ctx *ctx, size_t bytes);
       return me::fail((ctx), ME_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
   } while (0)
 
-// contiguous query range of this rank (sorted order of the query cloud)
+// contiguous range r of W over n items (tile lists; the point ranges of the sweeps come from query_shard, which snaps
+// them to cell boundaries)
 inline void shard_range(const me_ctx *ctx, long long n, long long *b, long long *e) {
   *b = n * ctx->rank / ctx->world;
   *e = n * (ctx->rank + 1) / ctx->world;
@@ -146,6 +152,7 @@ int compute_bbox(me_ctx *ctx, int which);
 int build_grid(me_ctx *ctx, int which);
 int build_both(me_ctx *ctx);
 int build_tiles(me_ctx *ctx, int which);
+int query_shard(me_ctx *ctx, int which, long long *b, long long *e);
 int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e);
 int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2);
 int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out);

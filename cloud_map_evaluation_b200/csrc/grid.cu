@@ -257,29 +257,40 @@ __global__ void __launch_bounds__(kThreads) rel_kernel(const P4 *__restrict__ so
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// query tiles (tile sweep only, built on demand): every kTileEdge^3 block of cells that holds at least one point
+// query tiles (tile sweep only, built on demand): every kTileEdge^3 block of cells that holds at least one point, in
+// increasing tile id (flag -> exclusive scan -> compaction: the same list on every rank, so that ranks can shard it)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) tile_list_kernel(const uint32_t *__restrict__ off, Lattice L,
-                                                             uint32_t *__restrict__ tiles,
-                                                             unsigned long long *__restrict__ n_tiles) {
+__global__ void __launch_bounds__(kThreads) tile_flag_kernel(const uint32_t *__restrict__ off, Lattice L,
+                                                             uint32_t *__restrict__ flag) {
   const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nt; t += (long long)gridDim.x * blockDim.x) {
-    const int bx = (int)(t % L.nb[0]), by = (int)((t / L.nb[0]) % L.nb[1]), bz = (int)(t / ((long long)L.nb[0] * L.nb[1]));
-    const int xa = bx * kTileEdge, xb = min(xa + kTileEdge, L.dims[0]);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t <= nt; t += (long long)gridDim.x * blockDim.x) {
     uint32_t tot = 0;
-    for (int dz = 0; dz < kTileEdge; ++dz) {
-      const int z = bz * kTileEdge + dz;
-      if (z >= L.dims[2]) break;
-      for (int dy = 0; dy < kTileEdge; ++dy) {
-        const int y = by * kTileEdge + dy;
-        if (y >= L.dims[1]) break;
-        const long long row = ((long long)z * L.dims[1] + y) * L.dims[0];
-        tot += __ldg(off + row + xb) - __ldg(off + row + xa);
+    if (t < nt) {
+      const int bx = (int)(t % L.nb[0]), by = (int)((t / L.nb[0]) % L.nb[1]), bz = (int)(t / ((long long)L.nb[0] * L.nb[1]));
+      const int xa = bx * kTileEdge, xb = min(xa + kTileEdge, L.dims[0]);
+      for (int dz = 0; dz < kTileEdge; ++dz) {
+        const int z = bz * kTileEdge + dz;
+        if (z >= L.dims[2]) break;
+        for (int dy = 0; dy < kTileEdge; ++dy) {
+          const int y = by * kTileEdge + dy;
+          if (y >= L.dims[1]) break;
+          const long long row = ((long long)z * L.dims[1] + y) * L.dims[0];
+          tot += __ldg(off + row + xb) - __ldg(off + row + xa);
+        }
       }
     }
-    if (tot) tiles[atomicAdd(n_tiles, 1ull)] = (uint32_t)t;
+    flag[t] = tot ? 1u : 0u;      // flag[nt] = 0: after the exclusive scan it holds the number of tiles
   }
 }
+__global__ void __launch_bounds__(kThreads) tile_compact_kernel(const uint32_t *__restrict__ pos, long long nt,
+                                                                uint32_t *__restrict__ tiles) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nt; t += (long long)gridDim.x * blockDim.x) {
+    const uint32_t p = __ldg(pos + t);
+    if (__ldg(pos + t + 1) != p) tiles[p] = (uint32_t)t;
+  }
+}
+
+static int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n);
 
 int build_tiles(me_ctx *ctx, int which) {
   Cloud &c = ctx->cloud[which];
@@ -287,16 +298,50 @@ int build_tiles(me_ctx *ctx, int which) {
   const Lattice &L = c.lat;
   const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
   ME_TRY(ensure(ctx, (void **)&c.d_tiles, &c.cap_tiles, std::min<long long>(nt, c.n), sizeof(uint32_t)));
-  unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
-  ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), ctx->stream));
-  const int blocks = (int)std::min<long long>((nt + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-  tile_list_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off, L, c.d_tiles, d_nt);
+  ME_TRY(ensure(ctx, (void **)&c.d_tile_pos, &c.cap_tile_pos, nt + 1, sizeof(uint32_t)));
+  const int blocks = (int)std::min<long long>((nt + kThreads) / kThreads, (long long)ctx->sm_count * 16);
+  tile_flag_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off, L, c.d_tile_pos);
   ME_LAUNCH_CHECK(ctx);
-  unsigned long long *h_nt = (unsigned long long *)ctx->h_pinned + 8;
-  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_TRY(exclusive_scan_inplace(ctx, c.d_tile_pos, nt + 1));
+  tile_compact_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_tile_pos, nt, c.d_tiles);
+  ME_LAUNCH_CHECK(ctx);
+  uint32_t *h_nt = (uint32_t *)((unsigned long long *)ctx->h_pinned + 8);
+  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, c.d_tile_pos + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  c.n_tiles = (long long)h_nt[0];
+  c.n_tiles = (long long)*h_nt;
   c.tiles_valid = true;
+  return ME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// query range of this rank: [n r / W, n (r+1) / W) of the cell-sorted order, snapped DOWN to cell boundaries.  The order
+// of the points inside a cell is not reproducible between ranks (the scatter takes its slots with atomics), the cell
+// boundaries are: with cell-aligned shards every point is evaluated by exactly one rank.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void shard_bounds_kernel(const P4 *__restrict__ sorted, const uint32_t *__restrict__ cell_off, long long n,
+                                    int rank, int world, unsigned long long *__restrict__ out) {
+  const int k = threadIdx.x;      // 0: begin, 1: end
+  if (k > 1) return;
+  const int r = rank + k;
+  long long b = n * r / world;
+  if (r >= world) b = n;
+  else if (b > 0) b = cell_off[cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(sorted + b) + 3)))];
+  out[k] = (unsigned long long)b;
+}
+
+int query_shard(me_ctx *ctx, int which, long long *b, long long *e) {
+  Cloud &c = ctx->cloud[which];
+  if (ctx->world == 1) { *b = 0; *e = c.n; return ME_OK; }
+  if (!(c.shard_valid && c.shard_rank == ctx->rank && c.shard_world == ctx->world)) {
+    unsigned long long *d = (unsigned long long *)ctx->d_scratch + 12, *h = (unsigned long long *)ctx->h_pinned + 12;
+    shard_bounds_kernel<<<1, 32, 0, ctx->stream>>>(c.d_sorted, c.d_cell_off, c.n, ctx->rank, ctx->world, d);
+    ME_LAUNCH_CHECK(ctx);
+    ME_CUDA(ctx, cudaMemcpyAsync(h, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    c.shard_b = (long long)h[0]; c.shard_e = (long long)h[1];
+    c.shard_rank = ctx->rank; c.shard_world = ctx->world; c.shard_valid = true;
+  }
+  *b = c.shard_b; *e = c.shard_e;
   return ME_OK;
 }
 
@@ -384,6 +429,20 @@ static bool pick_spec(const Cloud &c, const Cloud *other, double v_req, double h
   return false;
 }
 
+// in-place exclusive scan of n uint32 (3 phases; the tile partials live in the work buffer)
+static int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
+  const long long ntiles = (n + kScanTile - 1) / kScanTile;
+  ME_TRY(ensure_work(ctx, (size_t)ntiles * sizeof(uint32_t)));
+  uint32_t *tile = (uint32_t *)ctx->d_work;
+  scan_tile_sum_kernel<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(a, n, tile);
+  ME_LAUNCH_CHECK(ctx);
+  scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(tile, ntiles);
+  ME_LAUNCH_CHECK(ctx);
+  scan_apply_kernel<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(a, n, tile);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
 int build_grid(me_ctx *ctx, int which) {
   Cloud &c = ctx->cloud[which];
   Cloud &o = ctx->cloud[1 - which];
@@ -447,15 +506,7 @@ int build_grid(me_ctx *ctx, int which) {
   ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 
   // exclusive scan of the histogram, in place
-  long long ntiles = (L.ncells + kScanTile - 1) / kScanTile;
-  ME_TRY(ensure_work(ctx, (size_t)ntiles * sizeof(uint32_t)));
-  uint32_t *tile = (uint32_t *)ctx->d_work;
-  scan_tile_sum_kernel<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, tile);
-  ME_LAUNCH_CHECK(ctx);
-  scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(tile, ntiles);
-  ME_LAUNCH_CHECK(ctx);
-  scan_apply_kernel<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, tile);
-  ME_LAUNCH_CHECK(ctx);
+  ME_TRY(exclusive_scan_inplace(ctx, c.d_cell_off + 1, L.ncells));
 
   ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, c.n, sizeof(P4)));
   ME_TRY(ensure(ctx, (void **)&c.d_rel, &c.cap_rel, c.n, sizeof(float4)));
@@ -467,6 +518,7 @@ int build_grid(me_ctx *ctx, int which) {
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   c.max_cell_count = (long long)h_nt[2];
   c.tiles_valid = false;
+  c.shard_valid = false;
   c.grid_valid = true;
   c.nn_valid = false;
   c.entropy_valid = false;

@@ -186,7 +186,7 @@ __device__ __forceinline__ float gap2(int d, float u) {
   return g > 0.f ? g * g : 0.f;
 }
 
-template <int R, bool E16, bool U2>
+template <int R, bool E16, int U2>      // U2: 0 plain walk, 1 two candidates per iteration, 2 one-ahead software prefetch
 __global__ void __launch_bounds__(kFlatThreads)
 mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
                 const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
@@ -249,7 +249,19 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
     };
     RunWalk w;
     w.start(nrun);
-    if (U2) {
+    if (U2 == 2) {
+      uint32_t j0, jn = 0;
+      float y0, z0, yn = 0.f, zn = 0.f;
+      bool v = w.next(T, tid, h, qr.y, qr.z, R, j0, y0, z0);
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f), cn = c;
+      if (v) c = __ldg(rel + j0);
+      while (v) {
+        const bool vn = w.next(T, tid, h, qr.y, qr.z, R, jn, yn, zn);
+        if (vn) cn = __ldg(rel + jn);
+        process(c, y0, z0, j0);
+        c = cn; j0 = jn; y0 = yn; z0 = zn; v = vn;
+      }
+    } else if (U2 == 1) {
       for (;;) {
         uint32_t j0, j1;
         float y0, z0, y1, z1;
@@ -378,7 +390,7 @@ static int launch_plane(me_ctx *ctx, Cloud &c, long long qb, long long qe, const
   return ME_OK;
 }
 
-template <int R, bool E16, bool U2>
+template <int R, bool E16, int U2>
 static int launch_flat(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
   constexpr int NROW = (2 * R + 1) * (2 * R + 1);
   const size_t pad = getenv("ME_MME_PAD") ? (size_t)atoi(getenv("ME_MME_PAD")) : 0;   // tuning: fewer CTAs/SM, more L1
@@ -406,10 +418,12 @@ static int launch_flat_variant(me_ctx *ctx, Cloud &c, long long qb, long long qe
     case 1: return launch_plane<R, 1>(ctx, c, qb, qe, C, acc);
     case 2: return launch_plane<R, 2>(ctx, c, qb, qe, C, acc);
     case 4: return launch_plane<R, 4>(ctx, c, qb, qe, C, acc);
-    case 81: return launch_flat<R, false, false>(ctx, c, qb, qe, C, acc);
-    case 82: return launch_flat<R, false, true>(ctx, c, qb, qe, C, acc);
-    case 161: return launch_flat<R, true, false>(ctx, c, qb, qe, C, acc);
-    default: return launch_flat<R, true, true>(ctx, c, qb, qe, C, acc);
+    case 81: return launch_flat<R, false, 0>(ctx, c, qb, qe, C, acc);
+    case 83: return launch_flat<R, false, 2>(ctx, c, qb, qe, C, acc);
+    case 161: return launch_flat<R, true, 0>(ctx, c, qb, qe, C, acc);
+    case 162: return launch_flat<R, true, 1>(ctx, c, qb, qe, C, acc);
+    case 163: return launch_flat<R, true, 2>(ctx, c, qb, qe, C, acc);
+    default: return launch_flat<R, false, 1>(ctx, c, qb, qe, C, acc);
   }
 }
 
@@ -428,7 +442,7 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   ME_TRY(build_grid(ctx, which));
   StageTimer timer(ctx, which == ME_CLOUD_EST ? 4 : 5);
   long long qb, qe;
-  shard_range(ctx, c.n, &qb, &qe);               // contiguous range of the cell-sorted order
+  ME_TRY(query_shard(ctx, which, &qb, &qe));     // contiguous, cell-aligned range of the cell-sorted order
   ME_TRY(ensure(ctx, (void **)&c.d_entropy, &c.cap_entropy, c.n, sizeof(double)));
   MmeAcc *acc = (MmeAcc *)ctx->d_scratch;
   mme_init_kernel<<<1, 1, 0, ctx->stream>>>(acc);

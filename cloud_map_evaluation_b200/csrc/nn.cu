@@ -389,7 +389,7 @@ struct FlatGeom {
   double inv_h;
 };
 
-template <bool E16, bool U2>
+template <bool E16, int U2>      // U2: 0 plain walk, 1 two candidates per iteration, 2 one-ahead software prefetch
 __global__ void __launch_bounds__(kFlatThreads)
 nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
                const P4 *__restrict__ R, const float4 *__restrict__ rrel, const uint32_t *__restrict__ r_off,
@@ -402,7 +402,8 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
   const long long stride = (long long)gridDim.x * kFlatThreads;
   for (long long i = q_begin + blockIdx.x * (long long)kFlatThreads + tid; i < q_end; i += stride) {
     const float4 qr = __ldg(qrel + i);
-    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + i) + 3)));
+    const P4 q = load_p4(Q + i);      // needed after the walk only; issued here so its latency hides behind the walk
+    const uint32_t cq = cell_of(q.idx);
     const uint32_t cyz = cq / (uint32_t)G.qdimx;
     // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
     const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
@@ -441,7 +442,19 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
     };
     RunWalk w;
     w.start(nrun);
-    if (U2) {
+    if (U2 == 2) {
+      uint32_t j0, jn = 0;
+      float y0, z0, yn = 0.f, zn = 0.f;
+      bool v = w.next(T, tid, h, qr.y, qr.z, 1, j0, y0, z0);
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f), cn = c;
+      if (v) c = __ldg(rrel + j0);
+      while (v) {
+        const bool vn = w.next(T, tid, h, qr.y, qr.z, 1, jn, yn, zn);
+        if (vn) cn = __ldg(rrel + jn);
+        offer32(screen(c, y0, z0), j0);
+        c = cn; j0 = jn; y0 = yn; z0 = zn; v = vn;
+      }
+    } else if (U2 == 1) {
       for (;;) {
         uint32_t j0, jn;
         float y0, z0, y1, z1;
@@ -457,7 +470,6 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
       float y0, z0;
       while (w.next(T, tid, h, qr.y, qr.z, 1, j0, y0, z0)) offer32(screen(__ldg(rrel + j0), y0, z0), j0);
     }
-    const P4 q = load_p4(Q + i);
     Best b;
     b.init();
     if (b1 < INFINITY) {
@@ -660,6 +672,16 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   C.ref_maxabs = 0;
   for (int a = 0; a < 3; ++a) C.ref_maxabs = std::max(C.ref_maxabs, std::max(std::fabs(Rc.bbox_min[a]), std::fabs(Rc.bbox_max[a])));
 
+  // the flat kernel packs run lengths into 24 bits and x indices into an fp32 mantissa; otherwise the tile kernel runs
+  const bool use_tile = getenv("ME_NN_TILE") != nullptr || Qc.lat.dims[0] >= (1 << 24) || Rc.lat.dims[0] >= (1 << 24) ||
+                        3 * Rc.max_cell_count >= (1 << 24);
+  long long qb, qe, tb = 0, te = 0;
+  ME_TRY(query_shard(ctx, qwhich, &qb, &qe));  // flat sweep: contiguous, cell-aligned range of the cell-sorted query order
+  if (use_tile) {                              // (before the work buffer is carved up: the tile build scans in it)
+    ME_TRY(build_tiles(ctx, qwhich));
+    shard_range(ctx, Qc.n_tiles, &tb, &te);    // tile sweep: the (ordered) list of query tiles is sharded across ranks
+  }
+
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_idx, &Qc.cap_nn, Qc.n, sizeof(int32_t)));
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_d2, &Qc.cap_nn_d2, Qc.n, sizeof(double)));
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_sq, &Qc.cap_nn_sq, Qc.n, sizeof(double)));
@@ -682,15 +704,6 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   if (!attr_done) {
     ME_CUDA(ctx, cudaFuncSetAttribute(nn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     attr_done = true;
-  }
-  // the flat kernel packs run lengths into 24 bits and x indices into an fp32 mantissa; otherwise the tile kernel runs
-  const bool use_tile = getenv("ME_NN_TILE") != nullptr || Qc.lat.dims[0] >= (1 << 24) || Rc.lat.dims[0] >= (1 << 24) ||
-                        3 * Rc.max_cell_count >= (1 << 24);
-  long long qb, qe, tb = 0, te = 0;
-  shard_range(ctx, Qc.n, &qb, &qe);            // flat sweep: contiguous range of the cell-sorted query order
-  if (use_tile) {
-    ME_TRY(build_tiles(ctx, qwhich));
-    shard_range(ctx, Qc.n_tiles, &tb, &te);    // tile sweep: query tiles are sharded across ranks
   }
   if (use_tile ? te > tb : qe > qb) {
     if (use_tile) {
@@ -720,10 +733,12 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
                                                                     Rc.d_cell_off, Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,   \
                                                                     Qc.d_nn_sq, far_list, far_count)
       const size_t pad = getenv("ME_NN_PAD") ? (size_t)atoi(getenv("ME_NN_PAD")) : 0;   // tuning: extra smem = fewer CTAs/SM, more L1
-      if (code == 81) { ME_NN_FLAT_LAUNCH(false, false); }
-      else if (code == 82) { ME_NN_FLAT_LAUNCH(false, true); }
-      else if (code == 161) { ME_NN_FLAT_LAUNCH(true, false); }
-      else { ME_NN_FLAT_LAUNCH(true, true); }
+      if (code == 81) { ME_NN_FLAT_LAUNCH(false, 0); }
+      else if (code == 82) { ME_NN_FLAT_LAUNCH(false, 1); }
+      else if (code == 83) { ME_NN_FLAT_LAUNCH(false, 2); }
+      else if (code == 162) { ME_NN_FLAT_LAUNCH(true, 1); }
+      else if (code == 163) { ME_NN_FLAT_LAUNCH(true, 2); }
+      else { ME_NN_FLAT_LAUNCH(true, 0); }
 #undef ME_NN_FLAT_LAUNCH
     }
     ME_LAUNCH_CHECK(ctx);

@@ -271,20 +271,29 @@ def test_awd_negative_coordinates_and_no_pairs(api, O):
     assert none.n_pairs == 0 and np.isnan(none.awd) and np.isnan(none.scs)
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_shard_count_invariance(api, O, world):
-    """Sharding the query range over `world` contexts and summing the accumulators reproduces world = 1."""
+@pytest.mark.parametrize("tile", [False, True])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shard_count_invariance(api, O, world, tile):
+    """One context PER RANK (as in a multi-GPU job: every rank lays the clouds out itself, and the order of the points
+    inside a lattice cell differs from rank to rank because the scatter takes its slots with atomics).  The shards are
+    cell-aligned, so every point is evaluated by exactly one rank and the summed accumulators reproduce world = 1."""
+    import os
     est, gt, cfg = synth.make_pair("C1", scale=0.5)
     p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_AS_WRITTEN)
-    with _ctx(api, est, gt) as ctx:
-        ref = ctx.calculateMetricsWithInitialMatrix(p)
-        ref_m = ctx.eval_mme_accum(A.ME_CLOUD_EST, 0.1, 10)
+    if tile:
+        os.environ["ME_NN_TILE"] = "1"
+    try:
+        with _ctx(api, est, gt) as ctx:
+            ref = ctx.calculateMetricsWithInitialMatrix(p)
+            ref_m = ctx.eval_mme_accum(A.ME_CLOUD_EST, 0.1, 10)
         tot_e, tot_g, tot_m = A.me_nn_accum(), A.me_nn_accum(), A.me_mme_accum()
         tot_m.min_entropy, tot_m.max_entropy = np.inf, -np.inf
         for r in range(world):
-            ctx.set_shard(r, world)
-            e, g = ctx.eval_nn_accum(p)
-            m = ctx.eval_mme_accum(A.ME_CLOUD_EST, 0.1, 10)
+            # a different point order per rank: the caller order is permuted (indices are mapped back below)
+            perm_e = np.random.RandomState(100 + r).permutation(len(est))
+            with _ctx(api, est[perm_e], gt, rank=r, world=world) as ctx:
+                e, g = ctx.eval_nn_accum(p_geo := A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_GEOMETRIC))
+                m = ctx.eval_mme_accum(A.ME_CLOUD_EST, 0.1, 10)
             for tot, part in ((tot_e, e), (tot_g, g)):
                 for name, ctype in A.me_nn_accum._fields_:
                     v = getattr(part, name)
@@ -296,10 +305,15 @@ def test_shard_count_invariance(api, O, world):
             tot_m.n_query += m.n_query; tot_m.n_valid += m.n_valid; tot_m.sum_entropy += m.sum_entropy
             tot_m.min_entropy = min(tot_m.min_entropy, m.min_entropy)
             tot_m.max_entropy = max(tot_m.max_entropy, m.max_entropy)
-        got = ctx.nn_finalize(p, tot_e, tot_g)
+        with _ctx(api, est, gt) as ctx:
+            ref_geo = ctx.calculateMetricsWithInitialMatrix(p_geo)
+            got = ctx.nn_finalize(p_geo, tot_e, tot_g)
+    finally:
+        os.environ.pop("ME_NN_TILE", None)
     assert tot_e.n_query == len(est) and tot_g.n_query == len(gt)
-    _cmp_nn(got, ref)
-    assert tot_m.n_valid == ref_m.n_valid
+    _cmp_nn(got, ref_geo)
+    assert list(ref.est_to_gt.n_inlier) == list(ref_geo.est_to_gt.n_inlier)
+    assert tot_m.n_valid == ref_m.n_valid and tot_m.n_query == len(est)
     np.testing.assert_allclose(tot_m.sum_entropy, ref_m.sum_entropy, rtol=1e-12)
     assert (tot_m.min_entropy, tot_m.max_entropy) == (ref_m.min_entropy, ref_m.max_entropy)
 
