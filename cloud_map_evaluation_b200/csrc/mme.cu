@@ -186,12 +186,11 @@ __device__ __forceinline__ float gap2(int d, float u) {
   return g > 0.f ? g * g : 0.f;
 }
 
-template <int R, bool E16, int U2>      // U2: 0 plain walk, 1 two candidates per iteration, 2 one-ahead software prefetch
+template <int R, bool E16, int U2>      // U2: 0 plain walk, 1 two candidates (two loads in flight) per iteration
 __global__ void __launch_bounds__(kFlatThreads)
 mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
                 const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
                 MmeAcc *__restrict__ acc) {
-  constexpr int SIDE = 2 * R + 1;
   extern __shared__ __align__(16) unsigned char flat_smem[];
   RunTab<E16> T(flat_smem);
   const int tid = threadIdx.x;
@@ -249,19 +248,7 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
     };
     RunWalk w;
     w.start(nrun);
-    if (U2 == 2) {
-      uint32_t j0, jn = 0;
-      float y0, z0, yn = 0.f, zn = 0.f;
-      bool v = w.next(T, tid, h, qr.y, qr.z, R, j0, y0, z0);
-      float4 c = make_float4(0.f, 0.f, 0.f, 0.f), cn = c;
-      if (v) c = __ldg(rel + j0);
-      while (v) {
-        const bool vn = w.next(T, tid, h, qr.y, qr.z, R, jn, yn, zn);
-        if (vn) cn = __ldg(rel + jn);
-        process(c, y0, z0, j0);
-        c = cn; j0 = jn; y0 = yn; z0 = zn; v = vn;
-      }
-    } else if (U2 == 1) {
+    if (U2 == 1) {
       for (;;) {
         uint32_t j0, j1;
         float y0, z0, y1, z1;
@@ -282,149 +269,23 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
   flush_stats(ts, acc);
 }
 
-// plane variant: the run table holds only the 2R+1 rows of ONE dz plane (5 KB per CTA instead of 25 KB at R = 2, so the
-// L1 keeps its capacity and the register file, not shared memory, bounds the occupancy); the candidates of a plane are
-// walked flattened, lanes re-synchronise at the 2R+1 plane boundaries, and cz is a compile-time constant of the plane.
-template <int R, int U>
-__global__ void __launch_bounds__(kFlatThreads)
-mme_plane_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
-                 const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
-                 MmeAcc *__restrict__ acc) {
-  constexpr int SIDE = 2 * R + 1;
-  __shared__ uint2 tab[SIDE * kFlatThreads];      // [slot][thread] {begin, len << 8 | dy + R}
-  const int tid = threadIdx.x;
-  const float h = C.h, r2_lo = C.r2_lo, r2_hi = C.r2_hi;
-  ThreadStats ts;
-  ts.init();
-  const long long stride = (long long)gridDim.x * kFlatThreads;
-  for (long long i = q_begin + blockIdx.x * (long long)kFlatThreads + tid; i < q_end; i += stride) {
-    const float4 qr = __ldg(rel + i);
-    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + i) + 3)));
-    const int ix = (int)qr.w;
-    const uint32_t cyz = cq / (uint32_t)C.dimx;
-    const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
-    const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
-    float gl[R], gr[R];
-#pragma unroll
-    for (int d = 1; d <= R; ++d) { gl[d - 1] = gap2(-d, ux); gr[d - 1] = gap2(d, ux); }
-    Moments m;
-    m.init();
-#pragma unroll
-    for (int dz = -R; dz <= R; ++dz) {
-      const int z = iz + dz;
-      const float remz = C.rc2 - gap2(dz, uz);
-      const float cz = (float)dz * h - qr.z;
-      int nrun = 0;
-      if ((unsigned)z < (unsigned)C.dimz && remz >= 0.f) {
-#pragma unroll
-        for (int dy = -R; dy <= R; ++dy) {
-          const int y = iy + dy;
-          const float rem = remz - gap2(dy, uy);
-          int da = 0, db = 0;
-#pragma unroll
-          for (int d = 0; d < R; ++d) { da -= (gl[d] <= rem) ? 1 : 0; db += (gr[d] <= rem) ? 1 : 0; }
-          const int xa = max(ix + da, 0), xb = min(ix + db, C.dimx - 1);
-          uint32_t s = 0, e = 0;
-          if ((unsigned)y < (unsigned)C.dimy && rem >= 0.f) {
-            const uint32_t row = ((uint32_t)z * (uint32_t)C.dimy + (uint32_t)y) * (uint32_t)C.dimx;
-            s = __ldg(cell_off + row + xa);
-            e = __ldg(cell_off + row + xb + 1);
-          }
-          if (e > s) { tab[nrun * kFlatThreads + tid] = make_uint2(s, ((e - s) << 8) | (uint32_t)(dy + R)); ++nrun; }
-        }
-      }
-      auto process = [&](const float4 &c, float cy, uint32_t j) {
-        const float dx = fmaf(c.w - qr.w, h, c.x - qr.x), dy = c.y + cy, dzf = c.z + cz;
-        const float d2 = fmaf(dzf, dzf, fmaf(dy, dy, dx * dx));
-        if (d2 < r2_hi) {
-          bool in = true;
-          if (d2 > r2_lo) {
-            const P4 q = load_p4(S + i), p = load_p4(S + j);
-            in = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z) < C.r2;      // nanoflann RadiusResultSet: strict <
-          }
-          if (in) m.add((double)dx, (double)dy, (double)dzf);
-        }
-      };
-      uint32_t j = 0, e = 0;
-      int r = 0;
-      float cy = 0.f;
-      auto next = [&](uint32_t &idx, float &ocy) -> bool {
-        if (j >= e) {
-          if (r >= nrun) return false;
-          const uint2 t = tab[r * kFlatThreads + tid];
-          ++r;
-          j = t.x; e = t.x + (t.y >> 8);
-          cy = fmaf((float)((int)(t.y & 255u) - R), h, -qr.y);
-        }
-        idx = j++; ocy = cy;
-        return true;
-      };
-      for (;;) {
-        uint32_t jj[U];
-        float yy[U];
-        bool vv[U];
-        vv[0] = next(jj[0], yy[0]);
-        if (!vv[0]) break;
-#pragma unroll
-        for (int u = 1; u < U; ++u) { vv[u] = next(jj[u], yy[u]); if (!vv[u]) { jj[u] = jj[0]; yy[u] = yy[0]; } }
-        float4 cc[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) cc[u] = __ldg(rel + jj[u]);
-        process(cc[0], yy[0], jj[0]);
-#pragma unroll
-        for (int u = 1; u < U; ++u) if (vv[u]) process(cc[u], yy[u], jj[u]);
-      }
-    }
-    entropy_sorted[i] = finish_entropy(m, C.min_neighbors, ts);
-  }
-  flush_stats(ts, acc);
-}
-
-template <int R, int U>
-static int launch_plane(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
-  int per_sm = 64;
-  if (const char *b = getenv("ME_MME_BLOCKS")) per_sm = std::max(1, atoi(b));
-  const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * per_sm);
-  mme_plane_kernel<R, U><<<blocks, kFlatThreads, 0, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, c.d_entropy, acc);
-  ME_LAUNCH_CHECK(ctx);
-  return ME_OK;
-}
-
-template <int R, bool E16, int U2>
+template <int R>
 static int launch_flat(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
+  // measured on C3 (profiles/r01_kernel_variants.md): 8-byte table entries + two candidates per iteration
+  constexpr bool E16 = false;
+  constexpr int U2 = 1;
   constexpr int NROW = (2 * R + 1) * (2 * R + 1);
-  const size_t pad = getenv("ME_MME_PAD") ? (size_t)atoi(getenv("ME_MME_PAD")) : 0;   // tuning: fewer CTAs/SM, more L1
-  const size_t smem = (size_t)NROW * kFlatThreads * RunTab<E16>::kEntryBytes + pad;
+  const size_t smem = (size_t)NROW * kFlatThreads * RunTab<E16>::kEntryBytes;
   static bool attr_done = false;
   if (!attr_done) {
-    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  if (const char *co = getenv("ME_MME_CARVEOUT"))
-    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
-  int per_sm = 256;     // measured: 64 -> 4.83 ms, 256 -> 4.62 ms, 1024 -> 4.67 ms on C3
-  if (const char *b = getenv("ME_MME_BLOCKS")) per_sm = std::max(1, atoi(b));
-  const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * per_sm);
+  // fine-grained grid (~2 queries per thread): 64 CTAs/SM -> 4.83 ms, 256 -> 4.62 ms, 1024 -> 4.67 ms
+  const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 256);
   mme_flat_kernel<R, E16, U2><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, c.d_entropy, acc);
   ME_LAUNCH_CHECK(ctx);
   return ME_OK;
-}
-
-template <int R>
-static int launch_flat_variant(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
-  const char *v = getenv("ME_MME_VARIANT");     // tuning switch: "<entry bytes 8|16><unroll 1|2>", e.g. "162"
-  const int code = v ? atoi(v) : 82;
-  switch (code) {
-    case 1: return launch_plane<R, 1>(ctx, c, qb, qe, C, acc);
-    case 2: return launch_plane<R, 2>(ctx, c, qb, qe, C, acc);
-    case 4: return launch_plane<R, 4>(ctx, c, qb, qe, C, acc);
-    case 81: return launch_flat<R, false, 0>(ctx, c, qb, qe, C, acc);
-    case 83: return launch_flat<R, false, 2>(ctx, c, qb, qe, C, acc);
-    case 161: return launch_flat<R, true, 0>(ctx, c, qb, qe, C, acc);
-    case 162: return launch_flat<R, true, 1>(ctx, c, qb, qe, C, acc);
-    case 163: return launch_flat<R, true, 2>(ctx, c, qb, qe, C, acc);
-    default: return launch_flat<R, false, 1>(ctx, c, qb, qe, C, acc);
-  }
 }
 
 __global__ void unsort_f64_kernel(const P4 *__restrict__ S, long long n, const double *__restrict__ src,
@@ -474,9 +335,9 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
       C.r2_hi = (float)((C.r2 + band) * (1.0 + 1e-7));
       C.min_neighbors = min_neighbors;
       C.dimx = c.lat.dims[0]; C.dimy = c.lat.dims[1]; C.dimz = c.lat.dims[2];
-      if (rings == 1) ME_TRY(launch_flat_variant<1>(ctx, c, qb, qe, C, acc));
-      else if (rings == 2) ME_TRY(launch_flat_variant<2>(ctx, c, qb, qe, C, acc));
-      else ME_TRY(launch_flat_variant<3>(ctx, c, qb, qe, C, acc));
+      if (rings == 1) ME_TRY(launch_flat<1>(ctx, c, qb, qe, C, acc));
+      else if (rings == 2) ME_TRY(launch_flat<2>(ctx, c, qb, qe, C, acc));
+      else ME_TRY(launch_flat<3>(ctx, c, qb, qe, C, acc));
     } else {
       const int blocks = (int)std::min<long long>((qe - qb + kThreads - 1) / kThreads, (long long)ctx->sm_count * 64);
       mme_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, qb, qe, c.d_cell_off, c.lat, radius * radius, rc2, rings,

@@ -389,7 +389,7 @@ struct FlatGeom {
   double inv_h;
 };
 
-template <bool E16, int U2>      // U2: 0 plain walk, 1 two candidates per iteration, 2 one-ahead software prefetch
+template <bool E16, int U2>      // U2: 0 plain walk, 1 two candidates (two loads in flight) per iteration
 __global__ void __launch_bounds__(kFlatThreads)
 nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
                const P4 *__restrict__ R, const float4 *__restrict__ rrel, const uint32_t *__restrict__ r_off,
@@ -442,19 +442,7 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
     };
     RunWalk w;
     w.start(nrun);
-    if (U2 == 2) {
-      uint32_t j0, jn = 0;
-      float y0, z0, yn = 0.f, zn = 0.f;
-      bool v = w.next(T, tid, h, qr.y, qr.z, 1, j0, y0, z0);
-      float4 c = make_float4(0.f, 0.f, 0.f, 0.f), cn = c;
-      if (v) c = __ldg(rrel + j0);
-      while (v) {
-        const bool vn = w.next(T, tid, h, qr.y, qr.z, 1, jn, yn, zn);
-        if (vn) cn = __ldg(rrel + jn);
-        offer32(screen(c, y0, z0), j0);
-        c = cn; j0 = jn; y0 = yn; z0 = zn; v = vn;
-      }
-    } else if (U2 == 1) {
+    if (U2 == 1) {
       for (;;) {
         uint32_t j0, jn;
         float y0, z0, y1, z1;
@@ -725,21 +713,11 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(Qc.bbox_min[a]), std::fabs(Qc.bbox_max[a])));
       // per-axis offset error <= 1e-6 h + fp64 rounding of the cell origins (see mme.cu); vector norm <= sqrt(3) times that
       G.eta = (float)(1.7320508 * (1e-6 * Qc.lat.h + 4e-15 * maxabs));
-      const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * (getenv("ME_NN_BLOCKS") ? atoi(getenv("ME_NN_BLOCKS")) : 32));
-      const char *v = getenv("ME_NN_VARIANT");      // tuning switch: "<entry bytes 8|16><unroll 1|2>"
-      const int code = v ? atoi(v) : 161;
-#define ME_NN_FLAT_LAUNCH(E16, U2)                                                                                        \
-  nn_flat_kernel<E16, U2><<<grid, kFlatThreads, pad, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,  \
-                                                                    Rc.d_cell_off, Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,   \
-                                                                    Qc.d_nn_sq, far_list, far_count)
-      const size_t pad = getenv("ME_NN_PAD") ? (size_t)atoi(getenv("ME_NN_PAD")) : 0;   // tuning: extra smem = fewer CTAs/SM, more L1
-      if (code == 81) { ME_NN_FLAT_LAUNCH(false, 0); }
-      else if (code == 82) { ME_NN_FLAT_LAUNCH(false, 1); }
-      else if (code == 83) { ME_NN_FLAT_LAUNCH(false, 2); }
-      else if (code == 162) { ME_NN_FLAT_LAUNCH(true, 1); }
-      else if (code == 163) { ME_NN_FLAT_LAUNCH(true, 2); }
-      else { ME_NN_FLAT_LAUNCH(true, 0); }
-#undef ME_NN_FLAT_LAUNCH
+      const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 32);
+      // measured on C3 (profiles/r01_kernel_variants.md): 16-byte table entries, plain walk
+      nn_flat_kernel<true, 0><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
+                                                                      Rc.d_cell_off, Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                      Qc.d_nn_sq, far_list, far_count);
     }
     ME_LAUNCH_CHECK(ctx);
     nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C,

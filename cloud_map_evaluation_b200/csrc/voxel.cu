@@ -269,9 +269,11 @@ awd_kernel(Lattice Le, Lattice Lg, const int32_t *__restrict__ cnt_e, const doub
 }
 
 // ---- SCS: one warp per paired voxel, lanes over the (2R+1)^3 - 1 neighbour offsets (map_eval.cpp:351-387) -------
+template <int RADIUS>      // RADIUS > 0: compile-time neighbourhood (the reference hard-codes 5, map_eval.cpp:353); 0: run time
 __global__ void __launch_bounds__(kThreads)
-scs_kernel(Lattice Le, const double *__restrict__ w_vox, const uint32_t *__restrict__ pair_list, int radius,
+scs_kernel(Lattice Le, const double *__restrict__ w_vox, const uint32_t *__restrict__ pair_list, int radius_rt,
            AwdAcc *__restrict__ acc) {
+  const int radius = RADIUS > 0 ? RADIUS : radius_rt;
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -284,29 +286,47 @@ scs_kernel(Lattice Le, const double *__restrict__ w_vox, const uint32_t *__restr
     const int vx = (int)(vox % Le.nvox[0]);
     const int vy = (int)((vox / Le.nvox[0]) % Le.nvox[1]);
     const int vz = (int)(vox / ((long long)Le.nvox[0] * Le.nvox[1]));
+    // the lane's share of the (2R+1)^3 - 1 neighbour values is fetched once (all loads in flight together) and kept for
+    // both passes of the reference's mean / population-variance computation (map_eval.cpp:364-381)
+    constexpr int kMaxPerLane = 48;                  // radius <= 5: 1331 / 32 = 42 values per lane
+    double wv[kMaxPerLane];
+    const int per_lane = (total + 31) / 32;
+    const bool cached = per_lane <= kMaxPerLane;
     double sum = 0.0;
     int n = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      double mean = 0.0;
-      if (pass) { if (n == 0) break; mean = sum / (double)n; sum = 0.0; }
-      for (int t = lane; t < total; t += 32) {
-        const int dx = t / (side * side) - radius, dy = (t / side) % side - radius, dz = t % side - radius;
-        if (dx == 0 && dy == 0 && dz == 0) continue;
-        const int x = vx + dx, y = vy + dy, z = vz + dz;
-        if (x < 0 || x >= Le.nvox[0] || y < 0 || y >= Le.nvox[1] || z < 0 || z >= Le.nvox[2]) continue;
-        const double w = __ldg(w_vox + ((long long)z * Le.nvox[1] + y) * Le.nvox[0] + x);
-        if (isnan(w)) continue;
-        if (pass == 0) { sum += w; n++; } else sum += (w - mean) * (w - mean);
-      }
-      sum = warp_sum(sum);
-      if (pass == 0) {
+    auto fetch = [&](int t) -> double {
+      if (t >= total) return NAN;
+      const int dx = t / (side * side) - radius, dy = (t / side) % side - radius, dz = t % side - radius;
+      if (dx == 0 && dy == 0 && dz == 0) return NAN;
+      const int x = vx + dx, y = vy + dy, z = vz + dz;
+      if (x < 0 || x >= Le.nvox[0] || y < 0 || y >= Le.nvox[1] || z < 0 || z >= Le.nvox[2]) return NAN;
+      return __ldg(w_vox + ((long long)z * Le.nvox[1] + y) * Le.nvox[0] + x);
+    };
+    if (cached) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-      } else if (lane == 0) {
-        const double var = sum / (double)n;
-        l_scs += sqrt(var) / mean;
-        l_cnt++;
-      }
+      for (int k = 0; k < kMaxPerLane; ++k) wv[k] = k < per_lane ? fetch(lane + 32 * k) : NAN;
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) if (!isnan(wv[k])) { sum += wv[k]; n++; }
+    } else {
+      for (int t = lane; t < total; t += 32) { const double w = fetch(t); if (!isnan(w)) { sum += w; n++; } }
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (n == 0) continue;
+    const double mean = sum / (double)n;
+    double ss = 0.0;
+    if (cached) {
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) if (!isnan(wv[k])) ss += (wv[k] - mean) * (wv[k] - mean);
+    } else {
+      for (int t = lane; t < total; t += 32) { const double w = fetch(t); if (!isnan(w)) ss += (w - mean) * (w - mean); }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      const double var = ss / (double)n;
+      l_scs += sqrt(var) / mean;
+      l_cnt++;
     }
   }
   if (lane == 0 && l_cnt) { atomicAdd(&acc->sum_scs, l_scs); atomicAdd(&acc->n_scs, l_cnt); }
@@ -380,7 +400,8 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
   }
   {
     StageTimer timer(ctx, 8);
-    scs_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
+    if (scs_radius == 5) scs_kernel<5><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
+    else scs_kernel<0><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
     ME_LAUNCH_CHECK(ctx);
   }
   struct Host { AwdAcc a; char pad[256 - sizeof(AwdAcc)]; unsigned long long occ[2]; };
