@@ -99,6 +99,22 @@ class MapEvalB200:
         T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
         self._check(self._L.me_transform(self._ctx, which, T.ctypes.data_as(C.POINTER(C.c_double))))
 
+    def voxel_downsample(self, which, voxel_size):
+        """PointCloud::VoxelDownSample on the held cloud (map_eval.cpp:38-39); returns the new point count."""
+        n = C.c_int64(0)
+        self._check(self._L.me_voxel_downsample(self._ctx, which, float(voxel_size), C.byref(n)))
+        self.n[which] = n.value
+        self._keep[which] = None
+        return n.value
+
+    def get_cloud(self, which):
+        """The cloud currently held by the context as an (N, 3) float64 array."""
+        n = C.c_int64(0)
+        self._check(self._L.me_get_cloud(self._ctx, which, None, 0, C.byref(n)))
+        out = np.empty((n.value, 3), np.float64)
+        self._check(self._L.me_get_cloud(self._ctx, which, out.ctypes.data_as(C.POINTER(C.c_double)), n.value, C.byref(n)))
+        return out
+
     def build_grid(self, which):
         self._check(self._L.me_build_grid(self._ctx, which))
 

@@ -137,6 +137,7 @@ void me_destroy(me_ctx *ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->d_work) cudaFree(ctx->d_work);
+  if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
   for (int i = 0; i < 2 * ME_N_STAGE_TIMES; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -216,6 +217,27 @@ int me_transform(me_ctx *ctx, int which, const double T[16]) {
   ME_ENTER(ctx);
   if ((which != ME_CLOUD_EST && which != ME_CLOUD_GT) || !T) return fail(ctx, ME_ERR_INVALID, "bad arguments");
   return transform_cloud(ctx, which, T);
+}
+
+int me_voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad cloud id");
+  return voxel_downsample(ctx, which, voxel_size, n_out);
+}
+
+int me_get_cloud(me_ctx *ctx, int which, double *xyz_host, int64_t capacity_points, int64_t *n) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad cloud id");
+  Cloud &c = ctx->cloud[which];
+  if (n) *n = c.n;
+  if (!xyz_host) return ME_OK;                       // size query
+  if (capacity_points < c.n) return fail(ctx, ME_ERR_INVALID, "me_get_cloud: host buffer too small");
+  ME_TRY(wait_upload(ctx, which));
+  if (c.n > 0) {
+    ME_CUDA(ctx, cudaMemcpyAsync(xyz_host, c.d_xyz, (size_t)c.n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return ME_OK;
 }
 
 int me_build_grid(me_ctx *ctx, int which) {

@@ -99,6 +99,8 @@ struct me_ctx {
   // large device scratch (scan partials, far list, voxel tables)
   void *d_work = nullptr;
   size_t work_bytes = 0;
+  uint32_t *d_scan_tmp = nullptr;   // per-tile partials of exclusive_scan_inplace
+  long long cap_scan_tmp = 0;
   cudaEvent_t ev[2 * ME_N_STAGE_TIMES];
   bool ev_used[ME_N_STAGE_TIMES];
   int sm_count = 148;
@@ -153,6 +155,8 @@ int build_grid(me_ctx *ctx, int which);
 int build_both(me_ctx *ctx);
 int build_tiles(me_ctx *ctx, int which);
 int query_shard(me_ctx *ctx, int which, long long *b, long long *e);
+int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n);
+int voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out);
 int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e);
 int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2);
 int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out);

@@ -290,7 +290,6 @@ __global__ void __launch_bounds__(kThreads) tile_compact_kernel(const uint32_t *
   }
 }
 
-static int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n);
 
 int build_tiles(me_ctx *ctx, int which) {
   Cloud &c = ctx->cloud[which];
@@ -429,11 +428,12 @@ static bool pick_spec(const Cloud &c, const Cloud *other, double v_req, double h
   return false;
 }
 
-// in-place exclusive scan of n uint32 (3 phases; the tile partials live in the work buffer)
-static int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
+// in-place exclusive scan of n uint32 (3 phases; the per-tile partials live in a small buffer of their own, so callers
+// may keep data in the work buffer across the scan)
+int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
   const long long ntiles = (n + kScanTile - 1) / kScanTile;
-  ME_TRY(ensure_work(ctx, (size_t)ntiles * sizeof(uint32_t)));
-  uint32_t *tile = (uint32_t *)ctx->d_work;
+  ME_TRY(ensure(ctx, (void **)&ctx->d_scan_tmp, &ctx->cap_scan_tmp, ntiles, sizeof(uint32_t)));
+  uint32_t *tile = ctx->d_scan_tmp;
   scan_tile_sum_kernel<<<(unsigned)ntiles, kThreads, 0, ctx->stream>>>(a, n, tile);
   ME_LAUNCH_CHECK(ctx);
   scan_tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(tile, ntiles);

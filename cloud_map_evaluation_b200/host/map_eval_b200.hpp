@@ -204,7 +204,8 @@ class MapEvalB200 {
     return -1;
   }
   me_ctx *ctx_ = nullptr;
-  std::vector<double> map_3d_, gt_3d_;   // N x 3 fp64, the layout of open3d PointCloud::points_
+  std::vector<double> map_3d_, gt_3d_;   // N x 3 fp64, the layout of open3d PointCloud::points_ (as loaded)
+  int64_t n_est_ = 0, n_gt_ = 0;         // point counts after VoxelDownSample (the clouds the metrics see)
   double t1, t2, t3, t4, t5, t6, t7, t_fcd = 0.0, t_acc = 0.0;
   double t_vmd = 0.0, t_v = 0.0, t_cdf = 0.0, t_scs = 0.0;
   std::string subfolder, results_subfolder, results_file_path;
@@ -234,18 +235,6 @@ inline int MapEvalB200::process() {
     std::cerr << "ERROR: One or both point clouds are empty!" << std::endl;
     return -1;
   }
-  // map_eval.cpp:38-39 runs Open3D VoxelDownSample(downsample_size) here.  That pre-step is not part of the hot path
-  // built so far: clouds are evaluated as loaded.
-  if (param_.downsample_size > 0)
-    std::cout << "INFO: downsample_size = " << param_.downsample_size
-              << " ignored: voxel down-sampling is not built yet; feed clouds that are already down-sampled." << std::endl;
-
-  file_result << std::fixed << std::setprecision(15) << "Estimated-Ground Truth point count: " << map_3d_.size() / 3 << " / "
-              << gt_3d_.size() / 3 << std::endl;
-  if (param_.enable_debug)
-    std::cout << "INFO: Loaded point clouds: " << map_3d_.size() / 3 << " points (Map), " << gt_3d_.size() / 3
-              << " points (Ground Truth)." << std::endl;
-
   me_options opt{};
   opt.abi_version = ME_ABI_VERSION;
   opt.device = param_.gpu_device_;
@@ -254,6 +243,23 @@ inline int MapEvalB200::process() {
   if (me_create(&opt, &ctx_) != ME_OK) return fail("cannot create the B200 context");
   if (me_set_cloud(ctx_, ME_CLOUD_EST, map_3d_.data(), (int64_t)(map_3d_.size() / 3)) != ME_OK) return fail("me_set_cloud(est)");
   if (me_set_cloud(ctx_, ME_CLOUD_GT, gt_3d_.data(), (int64_t)(gt_3d_.size() / 3)) != ME_OK) return fail("me_set_cloud(gt)");
+
+  // map_3d_ = map_3d_->VoxelDownSample(param_.downsample_size); gt_3d_ likewise (map_eval.cpp:38-39), on the GPU.
+  // The reference calls it unconditionally (Open3D raises for voxel_size <= 0); a non-positive value skips the step here.
+  int64_t n_est = (int64_t)(map_3d_.size() / 3), n_gt = (int64_t)(gt_3d_.size() / 3);
+  if (param_.downsample_size > 0) {
+    if (me_voxel_downsample(ctx_, ME_CLOUD_EST, param_.downsample_size, &n_est) != ME_OK) return fail("me_voxel_downsample(est)");
+    if (me_voxel_downsample(ctx_, ME_CLOUD_GT, param_.downsample_size, &n_gt) != ME_OK) return fail("me_voxel_downsample(gt)");
+  } else {
+    std::cout << "INFO: downsample_size <= 0: clouds are evaluated as loaded." << std::endl;
+  }
+  n_est_ = n_est; n_gt_ = n_gt;
+
+  file_result << std::fixed << std::setprecision(15) << "Estimated-Ground Truth point count: " << n_est << " / " << n_gt
+              << std::endl;
+  if (param_.enable_debug)
+    std::cout << "INFO: Loaded point clouds: " << n_est << " points (Map), " << n_gt << " points (Ground Truth)."
+              << std::endl;
 
   if (param_.evaluate_mme_) {
     if (param_.enable_debug) std::cout << "INFO: Starting MME calculation..." << std::endl;

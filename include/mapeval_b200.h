@@ -159,6 +159,15 @@ ME_API int  me_set_cloud(me_ctx *ctx, int which, const double *xyz_host, int64_t
 ME_API int  me_set_cloud_device(me_ctx *ctx, int which, const double *xyz_device, int64_t n);
 /* replaces: map_3d_->Transform(initial_matrix) (map_eval.cpp:1206); T is a row-major 4x4 */
 ME_API int  me_transform(me_ctx *ctx, int which, const double T[16]);
+/* replaces: map_3d_ = map_3d_->VoxelDownSample(param_.downsample_size) and the same for gt_3d_ (map_eval.cpp:38-39;
+ * open3d::geometry::PointCloud::VoxelDownSample: voxel index floor((p - (min_bound - s/2)) / s), output = mean of the
+ * voxel's points accumulated in input order).  The cloud held by the context is replaced by its down-sampled version;
+ * *n_out (nullable) receives the new point count.  The output points are bit-identical to the CPU path as a set; they
+ * are ordered by increasing voxel index (Open3D: std::unordered_map iteration order, implementation-defined). */
+ME_API int  me_voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out);
+/* the cloud currently held by the context (after me_transform / me_voxel_downsample), caller order, N x 3 fp64.
+ * xyz_host == NULL: size query only (*n).  capacity_points < N is an error. */
+ME_API int  me_get_cloud(me_ctx *ctx, int which, double *xyz_host, int64_t capacity_points, int64_t *n);
 /* builds (or rebuilds) the cell-sorted grid of one cloud; the eval calls build lazily if needed */
 ME_API int  me_build_grid(me_ctx *ctx, int which);
 

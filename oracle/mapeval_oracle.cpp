@@ -677,4 +677,53 @@ int oracle_voxel_map(const double *xyz, int64_t n, double voxel_size, int64_t *n
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// [ext-vds] open3d::geometry::PointCloud::VoxelDownSample(voxel_size), called at map_eval.cpp:38-39 (Open3D 0.15-0.17,
+// PointCloud.cpp; not vendored under /root/reference): voxel_min_bound = GetMinBound() - 0.5 * voxel_size;
+// voxel index = int(floor((p - voxel_min_bound) / voxel_size)) per axis; points are accumulated per voxel in INPUT
+// order (AccumulatedPoint::AddPoint: point_ += p, num_of_points_++) and the output point is point_ / double(n).
+// Open3D emits the voxels in std::unordered_map iteration order (implementation-defined); here they are emitted in
+// increasing (ix, iy, iz) — the same SET of points, bit for bit.
+// ---------------------------------------------------------------------------------------------------
+int oracle_voxel_downsample(const double *xyz, int64_t n, double voxel_size, int64_t *n_out, double **out_xyz) {
+  *n_out = 0;
+  *out_xyz = nullptr;
+  if (n <= 0 || !(voxel_size > 0)) return -1;
+  double mn[3] = {xyz[0], xyz[1], xyz[2]};
+  for (int64_t i = 1; i < n; ++i)
+    for (int a = 0; a < 3; ++a) mn[a] = std::min(mn[a], xyz[3 * i + a]);
+  const double org[3] = {mn[0] - voxel_size * 0.5, mn[1] - voxel_size * 0.5, mn[2] - voxel_size * 0.5};
+  struct Acc { double s[3]; int64_t n; };
+  struct MixHasher {      // (Open3D's hash_eigen; any hash gives the same per-voxel sums — only the emission order depends on it)
+    std::size_t operator()(const Key3 &k) const {
+      uint64_t h = (uint64_t)(uint32_t)k.k[0] * 0x9E3779B97F4A7C15ull;
+      h = (h ^ (uint64_t)(uint32_t)k.k[1]) * 0xBF58476D1CE4E5B9ull;
+      h = (h ^ (uint64_t)(uint32_t)k.k[2]) * 0x94D049BB133111EBull;
+      return (std::size_t)(h ^ (h >> 29));
+    }
+  };
+  std::unordered_map<Key3, Acc, MixHasher> m;
+  m.reserve((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    Key3 k;
+    for (int a = 0; a < 3; ++a) k.k[a] = (int)std::floor((xyz[3 * i + a] - org[a]) / voxel_size);
+    auto it = m.find(k);
+    if (it == m.end()) it = m.emplace(k, Acc{{0.0, 0.0, 0.0}, 0}).first;
+    for (int a = 0; a < 3; ++a) it->second.s[a] += xyz[3 * i + a];
+    it->second.n++;
+  }
+  std::vector<std::pair<Key3, Acc>> v(m.begin(), m.end());
+  std::sort(v.begin(), v.end(), [](const std::pair<Key3, Acc> &a, const std::pair<Key3, Acc> &b) {
+    if (a.first.k[0] != b.first.k[0]) return a.first.k[0] < b.first.k[0];
+    if (a.first.k[1] != b.first.k[1]) return a.first.k[1] < b.first.k[1];
+    return a.first.k[2] < b.first.k[2];
+  });
+  double *o = (double *)std::malloc(std::max<size_t>(1, v.size()) * 3 * sizeof(double));
+  for (size_t i = 0; i < v.size(); ++i)
+    for (int a = 0; a < 3; ++a) o[3 * i + a] = v[i].second.s[a] / (double)v[i].second.n;
+  *n_out = (int64_t)v.size();
+  *out_xyz = o;
+  return 0;
+}
+
 }  // extern "C"

@@ -44,6 +44,7 @@ def lib():
         L.oracle_scs.argtypes = [ip, dp, C.c_int64, C.c_int, dp, C.POINTER(C.c_int64)]
         L.oracle_voxel_map.argtypes = [dp, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.POINTER(ip),
                                        C.POINTER(ip), C.POINTER(dp), C.POINTER(dp)]
+        L.oracle_voxel_downsample.argtypes = [dp, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.POINTER(dp)]
         _lib = L
     return _lib
 
@@ -151,3 +152,16 @@ def voxel_map(xyz, voxel_size):
     for ptr in (kp, cp, mp, sp):
         lib().oracle_free(ptr)
     return keys, counts, mu, sigma
+
+
+def voxel_downsample(xyz, voxel_size):
+    """open3d PointCloud::VoxelDownSample (map_eval.cpp:38-39); output voxels in increasing (ix, iy, iz)."""
+    a = _cloud(xyz)
+    n_out = C.c_int64(0)
+    out = C.POINTER(C.c_double)()
+    rc = lib().oracle_voxel_downsample(_dptr(a), a.shape[0], float(voxel_size), C.byref(n_out), C.byref(out))
+    if rc != 0:
+        raise ValueError("oracle_voxel_downsample failed")
+    res = np.ctypeslib.as_array(out, shape=(n_out.value, 3)).copy()
+    lib().oracle_free(out)
+    return res

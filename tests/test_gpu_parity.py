@@ -257,6 +257,18 @@ def test_awd_scs_parity(api, O, hint):
     np.testing.assert_allclose(a[:, 21:27], b[:, 21:27], rtol=1e-7, atol=1e-16)
 
 
+@pytest.mark.parametrize("radius,min_points", [(1, 100), (2, 40), (7, 100)])
+def test_scs_other_radii_and_point_filters(api, O, radius, min_points):
+    """SCS neighbourhoods other than the reference's hard-coded 5 (generic kernel; radius 7 exceeds the per-lane cache)."""
+    est, gt, cfg = synth.make_pair("C2", scale=0.2)
+    v = cfg["vmd_voxel_size"]
+    with _ctx(api, est, gt, vmd_voxel_size=v) as ctx:
+        got = ctx.calculateVMD(v, min_points, radius)
+    exp = O.eval_awd(est, gt, v, min_points, radius)
+    assert (got.n_pairs, got.n_scs) == (exp.n_pairs, exp.n_scs) and got.n_pairs > 50
+    np.testing.assert_allclose([got.awd, got.scs], [exp.awd, exp.scs], rtol=RTOL)
+
+
 def test_awd_negative_coordinates_and_no_pairs(api, O):
     est, gt, _ = synth.make_pair("C1", scale=0.5)
     est = est - 7.3
@@ -361,3 +373,32 @@ def test_unaligned_device_buffer_and_extreme_points(api, O, n_est):
         ctx.set_cloud_device(A.ME_CLOUD_GT, tg.data_ptr(), len(gt), keepalive=tg)
         got = ctx.calculateMetricsWithInitialMatrix(p)
     _cmp_nn(got, exp)
+
+
+@pytest.mark.parametrize("voxel", [0.01, 0.05, 0.3])
+def test_voxel_downsample_matches_open3d_semantics(api, O, voxel):
+    """me_voxel_downsample vs the oracle's restatement of PointCloud::VoxelDownSample: the same SET of output points,
+    bit for bit (sums in input order, division by the count); the oracle emits in voxel order too."""
+    est, gt, cfg = synth.make_pair("C2", scale=0.1)
+    est = est - np.array([250.0, -1000.0, 3.0])                  # negative / large coordinates
+    est = np.ascontiguousarray(np.concatenate([est, est[:500]]))  # exact duplicates share a voxel
+    with _ctx(api, est, gt) as ctx:
+        n = ctx.voxel_downsample(A.ME_CLOUD_EST, voxel)
+        got = ctx.get_cloud(A.ME_CLOUD_EST)
+        # the path runs on the down-sampled cloud afterwards
+        p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+        nn = ctx.calculateMetricsWithInitialMatrix(p)
+    exp = O.voxel_downsample(est, voxel)
+    assert n == len(exp) == len(got)
+    np.testing.assert_array_equal(got, exp)
+    _cmp_nn(nn, O.eval_nn(exp, gt, p))
+
+
+def test_voxel_downsample_errors(api):
+    est, gt, cfg = synth.make_pair("C1", scale=0.01)
+    with _ctx(api, est, gt) as ctx:
+        with pytest.raises(api.MapEvalError):
+            ctx.voxel_downsample(A.ME_CLOUD_EST, 0.0)
+        with pytest.raises(api.MapEvalError):
+            ctx.voxel_downsample(A.ME_CLOUD_EST, 1e-7)             # more than 2^21 voxels per axis
+        assert ctx.voxel_downsample(A.ME_CLOUD_EST, 100.0) == 1    # everything in one voxel

@@ -190,3 +190,38 @@ def test_map_eval_end_to_end(exe, tmp_path):
     cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false"))
     out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
     assert out.returncode != 0 and "ICP" in out.stderr
+
+
+@pytest.mark.gpu
+def test_map_eval_with_downsampling(exe, tmp_path):
+    """downsample_size > 0 (every shipped config uses 0.01): VoxelDownSample runs on the GPU before the metric path
+    (map_eval.cpp:38-39).  The down-sampled clouds come out in voxel order, so the oracle is fed the oracle's own
+    down-sampling of the same input (same point set; only order-dependent quantities are excluded)."""
+    from cloud_map_evaluation_b200 import _abi as A
+    from cloud_map_evaluation_b200 import synth
+    from oracle import oracle as O
+    est, gt, cfg = synth.make_pair("C2", scale=0.1)
+    est_dir = tmp_path / "est"
+    est_dir.mkdir()
+    _write_pcd(str(est_dir / "map.pcd"), est, "binary")
+    _write_pcd(str(tmp_path / "gt.pcd"), gt, "binary")
+    s = 0.03
+    text = CONFIG.format(est=str(est_dir), gt=str(tmp_path / "gt.pcd"), gt_mme="false", initial="true")
+    text = text.replace("[1.0, 0.0, 0.0, 0.5]", "[1.0, 0.0, 0.0, 0.0]").replace("[0.0, 0.0, 1.0, -2]", "[0.0, 0.0, 1.0, 0.0]")
+    text = text.replace("downsample_size: 0.0", f"downsample_size: {s}")
+    cfgp = tmp_path / "config.yaml"
+    cfgp.write_text(text)
+    out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = (est_dir / "map_results" / "map_results.txt").read_text().splitlines()
+    line = {l.split(":")[0]: l.split(":", 1)[1].split() for l in res if ":" in l}
+    de, dg = O.voxel_downsample(est, s), O.voxel_downsample(gt, s)
+    assert len(de) < len(est) and len(dg) < len(gt)
+    assert line["Estimated-Ground Truth point count"] == [str(len(de)), "/", str(len(dg))]
+    onn = O.eval_nn(de, dg, A.make_nn_params([0.2, 0.1, 0.08, 0.05, 0.01], 1.0))
+    np.testing.assert_allclose([float(x) for x in line["RMSE/AC"]], list(onn.est_to_gt.rmse), rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose([float(x) for x in line["Comp"]], list(onn.est_to_gt.fitness), rtol=1e-12)
+    me = O.eval_mme(de, 0.1, 10)
+    assert abs(float(line["MME"][0]) - me.mme) < 6e-6
+    oawd = O.eval_awd(de, dg, 0.25, 100, 5)
+    assert abs(float(line["VMD"][0]) - oawd.awd) < 6e-6 and abs(float(line["SCS"][0]) - oawd.scs) < 6e-6

@@ -174,3 +174,19 @@ def test_voxel_gaussians_and_awd_against_numpy():
     ek = np.unique(np.floor(est / v).astype(np.int64), axis=0)
     es, gs = {tuple(k) for k in ek}, {tuple(k) for k in uk}
     assert (res.n_active, res.n_old, res.n_new) == (len(es & gs), len(gs - es), len(es - gs))
+
+
+def test_voxel_downsample_against_numpy():
+    """oracle_voxel_downsample vs an independent numpy statement of Open3D's VoxelDownSample."""
+    rng = np.random.RandomState(11)
+    p = rng.rand(30000, 3) * np.array([4.0, 2.0, 1.0]) - np.array([100.0, 0.5, -7.0])
+    for s in (0.02, 0.11, 0.9):
+        o = O.voxel_downsample(p, s)
+        org = p.min(0) - 0.5 * s
+        k = np.floor((p - org) / s).astype(np.int64)
+        u, inv = np.unique(k, axis=0, return_inverse=True)
+        sums = np.zeros((len(u), 3))
+        np.add.at(sums, inv.ravel(), p)          # np.add.at accumulates in input order, like AccumulatedPoint::AddPoint
+        m = sums / np.bincount(inv.ravel())[:, None]
+        assert o.shape == m.shape
+        np.testing.assert_array_equal(o, m)      # np.unique sorts rows lexicographically = increasing (ix, iy, iz)
