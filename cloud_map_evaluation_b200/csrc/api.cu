@@ -46,7 +46,7 @@ int ensure_work(me_ctx *ctx, size_t bytes) {
 }
 
 static void invalidate(Cloud &c) {
-  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false;
+  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false; c.entropy_caller_valid = false;
 }
 
 static void free_cloud(Cloud &c) {
@@ -59,6 +59,7 @@ static void free_cloud(Cloud &c) {
   if (c.d_nn_d2) cudaFree(c.d_nn_d2);
   if (c.d_nn_sq) cudaFree(c.d_nn_sq);
   if (c.d_entropy) cudaFree(c.d_entropy);
+  if (c.d_entropy_caller) cudaFree(c.d_entropy_caller);
   if (c.d_tiles) cudaFree(c.d_tiles);
   if (c.d_tile_pos) cudaFree(c.d_tile_pos);
   if (c.upload_done) cudaEventDestroy(c.upload_done);
@@ -163,6 +164,7 @@ int me_set_shard(me_ctx *ctx, int32_t rank, int32_t world) {
   ctx->rank = rank; ctx->world = world;
   ctx->cloud[0].nn_valid = ctx->cloud[1].nn_valid = false;
   ctx->cloud[0].entropy_valid = ctx->cloud[1].entropy_valid = false;
+  ctx->cloud[0].entropy_caller_valid = ctx->cloud[1].entropy_caller_valid = false;
   ctx->cloud[0].shard_valid = ctx->cloud[1].shard_valid = false;
   return ME_OK;
 }

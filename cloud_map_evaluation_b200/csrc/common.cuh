@@ -42,6 +42,8 @@ struct Cloud {
   bool owned = false;
   long long cap_xyz = 0;
   bool grid_valid = false;
+  bool grid_solo = false;       // the lattice is this cloud's own (MME with a large radius), not the shared voxel-aligned one
+  double solo_h = 0.0;
   double bbox_min[3], bbox_max[3];
   bool bbox_valid = false;
   Lattice lat;
@@ -71,9 +73,12 @@ struct Cloud {
   double *d_nn_sq = nullptr;        // squared norm as Eigen accumulates it (inlier statistics)
   long long cap_nn = 0, cap_nn_d2 = 0, cap_nn_sq = 0;
   bool nn_valid = false;
-  double *d_entropy = nullptr;
+  double *d_entropy = nullptr;      // sorted order of the lattice the MME sweep ran on
   long long cap_entropy = 0;
   bool entropy_valid = false;
+  double *d_entropy_caller = nullptr;   // caller order, kept when the sweep ran on a solo lattice (which the next build replaces)
+  long long cap_entropy_caller = 0;
+  bool entropy_caller_valid = false;
 };
 
 }  // namespace me
@@ -151,7 +156,8 @@ struct StageTimer {
 // stage entry points (implemented in grid.cu / nn.cu / mme.cu / voxel.cu)
 int wait_upload(me_ctx *ctx, int which);
 int compute_bbox(me_ctx *ctx, int which);
-int build_grid(me_ctx *ctx, int which);
+int build_grid(me_ctx *ctx, int which, double solo_h = 0.0);
+double density_edge(const Cloud &c);
 int build_both(me_ctx *ctx);
 int build_tiles(me_ctx *ctx, int which);
 int query_shard(me_ctx *ctx, int which, long long *b, long long *e);

@@ -114,7 +114,7 @@ int voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out) 
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the old buffer may be released (or handed back) now
   if (c.owned && c.d_xyz) cudaFree(c.d_xyz);
   c.d_xyz = out; c.cap_xyz = cap_out; c.owned = true; c.n = nv;
-  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false;
+  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false; c.entropy_caller_valid = false;
   if (n_out) *n_out = nv;
   return ME_OK;
 }

@@ -395,7 +395,7 @@ static int occupancy(me_ctx *ctx, Cloud &c, const Lattice &L, long long *occupie
 }
 
 // h the cloud would like on its own: ~2 points per cell for a volume-filling cloud
-static double density_edge(const Cloud &c) {
+double density_edge(const Cloud &c) {
   double ext[3], vol = 1.0, ext_max = 0.0;
   for (int a = 0; a < 3; ++a) { ext[a] = c.bbox_max[a] - c.bbox_min[a]; ext_max = std::max(ext_max, ext[a]); }
   if (ext_max <= 0.0) ext_max = 1.0;
@@ -443,12 +443,16 @@ int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
   return ME_OK;
 }
 
-int build_grid(me_ctx *ctx, int which) {
+// solo_h > 0: lay the cloud out on a lattice of its own with cells of (about) that edge — used by the MME sweep when the
+// search radius spans many cells of the shared lattice (mme.cu).  A solo lattice is not voxel-aligned and not shared with
+// the other cloud; the next ordinary build_grid() replaces it.
+int build_grid(me_ctx *ctx, int which, double solo_h) {
   Cloud &c = ctx->cloud[which];
   Cloud &o = ctx->cloud[1 - which];
   if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
   if (c.n >= 0x7fffffffll) return fail(ctx, ME_ERR_RANGE, "more than 2^31-1 points per cloud (the reference indexes with int)");
-  if (c.grid_valid) return ME_OK;
+  const bool solo = solo_h > 0;
+  if (c.grid_valid && c.grid_solo == solo && (!solo || c.solo_h == solo_h)) return ME_OK;
   ME_TRY(wait_upload(ctx, which));
   StageTimer timer(ctx, which == ME_CLOUD_EST ? 0 : 1);
   ME_TRY(compute_bbox(ctx, which));
@@ -457,16 +461,19 @@ int build_grid(me_ctx *ctx, int which) {
 
   // Both clouds share one lattice spec (v, m) so that their cells coincide.  The spec is re-planned whenever no
   // valid grid depends on it (i.e. at the first build of a pass); a later build re-uses it.
-  bool planned_here = false;
   Lattice L;
-  if (o.grid_valid && ctx->spec_m > 0 && (v_req <= 0 || ctx->spec_v == v_req) &&
-      make_lattice(c, ctx->spec_v, ctx->spec_m, budget, &L)) {
+  if (solo) {
+    double v; int m;
+    if (!pick_spec(c, nullptr, 0.0, solo_h, budget, &v, &m, &L))
+      return fail(ctx, ME_ERR_RANGE, "cannot fit the cloud into the dense lattice budget");
+    ME_TRY(histogram(ctx, c, L));
+  } else if (o.grid_valid && !o.grid_solo && ctx->spec_m > 0 && (v_req <= 0 || ctx->spec_v == v_req) &&
+             make_lattice(c, ctx->spec_v, ctx->spec_m, budget, &L)) {
     ME_TRY(histogram(ctx, c, L));
   } else {
-    if (o.grid_valid) {   // the other grid's spec cannot host this cloud: both are laid out again
+    if (o.grid_valid && !o.grid_solo) {   // the other grid's spec cannot host this cloud: both are laid out again
       o.grid_valid = false; o.nn_valid = false; o.entropy_valid = false;
     }
-    planned_here = true;
     const Cloud *other = (o.n > 0 && o.bbox_valid) ? &o : nullptr;
     double h_target = ctx->nn_cell_size > 0 ? ctx->nn_cell_size : density_edge(c);
     bool have = false;
@@ -491,7 +498,8 @@ int build_grid(me_ctx *ctx, int which) {
       h_target = h_new;
     }
   }
-  (void)planned_here;
+  c.grid_solo = solo;
+  c.solo_h = solo ? solo_h : 0.0;
   c.lat = L;
 
   // scratch slots: [9] occupied cells, [10] largest cell (bounds the run lengths of the sweeps)
@@ -552,7 +560,7 @@ int transform_cloud(me_ctx *ctx, int which, const double T[16]) {
   int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
   transform_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, M);
   ME_LAUNCH_CHECK(ctx);
-  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false;
+  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false; c.entropy_caller_valid = false;
   return ME_OK;
 }
 

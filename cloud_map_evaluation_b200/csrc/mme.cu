@@ -269,6 +269,103 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
   flush_stats(ts, acc);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// plane kernel (3 < rings <= kMaxPlaneRings): the same fp32-screened walk for radii spanning many cells (e.g. r = 1.0 m
+// on a ~0.15 m lattice).  The run table holds the 2R+1 rows of ONE dz plane at a time (a full (2R+1)^2 table would not
+// fit), the candidates of a plane are walked flattened, lanes re-synchronise at the plane boundaries — cheap here,
+// because with many cells per radius every row run holds many candidates.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kMaxPlaneRings = 15;
+
+__global__ void __launch_bounds__(kFlatThreads)
+mme_plane_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
+                 const uint32_t *__restrict__ cell_off, MmeConst C, int R, double *__restrict__ entropy_sorted,
+                 MmeAcc *__restrict__ acc) {
+  extern __shared__ __align__(16) unsigned char flat_smem[];
+  uint2 *tab = reinterpret_cast<uint2 *>(flat_smem);      // [slot][thread] {begin, len << 8 | dy + R}
+  const int tid = threadIdx.x;
+  const float h = C.h, r2_lo = C.r2_lo, r2_hi = C.r2_hi;
+  ThreadStats ts;
+  ts.init();
+  const long long stride = (long long)gridDim.x * kFlatThreads;
+  for (long long i = q_begin + blockIdx.x * (long long)kFlatThreads + tid; i < q_end; i += stride) {
+    const float4 qr = __ldg(rel + i);
+    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + i) + 3)));
+    const int ix = (int)qr.w;
+    const uint32_t cyz = cq / (uint32_t)C.dimx;
+    const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
+    const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
+    Moments m;
+    m.init();
+    for (int dz = -R; dz <= R; ++dz) {
+      const int z = iz + dz;
+      const float remz = C.rc2 - gap2(dz, uz);
+      const float cz = (float)dz * h - qr.z;
+      int nrun = 0;
+      if ((unsigned)z < (unsigned)C.dimz && remz >= 0.f) {
+        for (int dy = -R; dy <= R; ++dy) {
+          const int y = iy + dy;
+          const float rem = remz - gap2(dy, uy);
+          if ((unsigned)y >= (unsigned)C.dimy || rem < 0.f) continue;
+          // cells d steps to the left have gap ux + d - 1, to the right d - ux: keep those with gap <= sqrt(rem) (+ slack)
+          const float xw = sqrtf(rem) + 1e-3f;
+          const int da = -min(R, max(0, (int)floorf(xw - ux + 1.f))), db = min(R, max(0, (int)floorf(xw + ux)));
+          const int xa = max(ix + da, 0), xb = min(ix + db, C.dimx - 1);
+          const uint32_t row = ((uint32_t)z * (uint32_t)C.dimy + (uint32_t)y) * (uint32_t)C.dimx;
+          const uint32_t s = __ldg(cell_off + row + xa), e = __ldg(cell_off + row + xb + 1);
+          if (e > s) { tab[nrun * kFlatThreads + tid] = make_uint2(s, ((e - s) << 8) | (uint32_t)(dy + R)); ++nrun; }
+        }
+      }
+      uint32_t j = 0, e = 0;
+      int r = 0;
+      float cy = 0.f;
+      auto next = [&](uint32_t &idx, float &ocy) -> bool {
+        if (j >= e) {
+          if (r >= nrun) return false;
+          const uint2 t = tab[r * kFlatThreads + tid];
+          ++r;
+          j = t.x; e = t.x + (t.y >> 8);
+          cy = fmaf((float)((int)(t.y & 255u) - R), h, -qr.y);
+        }
+        idx = j++; ocy = cy;
+        return true;
+      };
+      auto process = [&](const float4 &c, float cyv, uint32_t jj) {
+        const float dx = fmaf(c.w - qr.w, h, c.x - qr.x), dy = c.y + cyv, dzf = c.z + cz;
+        const float d2 = fmaf(dzf, dzf, fmaf(dy, dy, dx * dx));
+        if (d2 < r2_hi) {
+          bool in = true;
+          if (d2 > r2_lo) {
+            const P4 q = load_p4(S + i), p = load_p4(S + jj);
+            in = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z) < C.r2;      // nanoflann RadiusResultSet: strict <
+          }
+          if (in) m.add((double)dx, (double)dy, (double)dzf);
+        }
+      };
+      for (;;) {
+        uint32_t j0, j1;
+        float y0, y1;
+        if (!next(j0, y0)) break;
+        const bool v1 = next(j1, y1);
+        const float4 c0 = __ldg(rel + j0);
+        const float4 c1 = __ldg(rel + (v1 ? j1 : j0));
+        process(c0, y0, j0);
+        if (v1) process(c1, y1, j1);
+      }
+    }
+    entropy_sorted[i] = finish_entropy(m, C.min_neighbors, ts);
+  }
+  flush_stats(ts, acc);
+}
+
+static int launch_plane(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, int rings, MmeAcc *acc) {
+  const size_t smem = (size_t)(2 * rings + 1) * kFlatThreads * sizeof(uint2);
+  const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 64);
+  mme_plane_kernel<<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, rings, c.d_entropy, acc);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
 template <int R>
 static int launch_flat(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
   // measured on C3 (profiles/r01_kernel_variants.md): 8-byte table entries + two candidates per iteration
@@ -300,7 +397,22 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   Cloud &c = ctx->cloud[which];
   if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
   if (!(radius > 0)) return fail(ctx, ME_ERR_INVALID, "nn_radius must be > 0");
-  ME_TRY(build_grid(ctx, which));
+  // Lattice for this radius.  The shared lattice is tuned for the 1-NN sweeps (~2 points per occupied cell); when the
+  // radius spans more than 3 of its cells (dense surfaces: 1 cm spacing, r = 0.1 m -> 7 cells; or r = 1.0 m), most of
+  // the (2R+1)^2 rows of a neighbourhood are empty and enumerating them dominates.  The cloud is then laid out on a
+  // lattice of its own with h = r/2 (rings = 2) for this sweep; the next NN / voxel stage lays it out again.
+  ME_TRY(wait_upload(ctx, which));
+  ME_TRY(compute_bbox(ctx, which));
+  bool solo = false;
+  if (!getenv("ME_MME_SHARED_LATTICE")) {
+    const double h_now = (c.grid_valid && !c.grid_solo) ? c.lat.h : (ctx->nn_cell_size > 0 ? ctx->nn_cell_size : density_edge(c));
+    solo = radius / h_now > 3.0 + 1e-9;
+    if (!solo && !(c.grid_valid && !c.grid_solo)) {      // the estimate may be refined downwards by the build
+      ME_TRY(build_grid(ctx, which));
+      solo = radius / c.lat.h > 3.0 + 1e-9;
+    }
+  }
+  ME_TRY(build_grid(ctx, which, solo ? 0.5 * radius : 0.0));
   StageTimer timer(ctx, which == ME_CLOUD_EST ? 4 : 5);
   long long qb, qe;
   ME_TRY(query_shard(ctx, which, &qb, &qe));     // contiguous, cell-aligned range of the cell-sorted order
@@ -317,19 +429,20 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   const float rc2 = (float)(rc * rc * (1.0 + 1e-5) + 1e-4);   // row pruning is conservative; the point test decides
   if (qe > qb) {
     // the flat kernel packs run lengths into 24 bits and x indices into an fp32 mantissa
-    const bool flat = rings <= 3 && c.lat.dims[0] < (1 << 24) && (2 * rings + 1) * c.max_cell_count < (1 << 24) &&
-                      !getenv("ME_MME_WALK");
+    const bool flat = rings <= kMaxPlaneRings && c.lat.dims[0] < (1 << 24) &&
+                      (2 * rings + 1) * c.max_cell_count < (1 << 24) && !getenv("ME_MME_WALK");
     if (flat) {
       MmeConst C;
       C.h = (float)c.lat.h; C.inv_h = (float)(1.0 / c.lat.h);
       C.rc2 = rc2;
       C.r2 = radius * radius;
-      // fp32 screening error: |offset error| <= E per axis (cell-relative rounding 2^-24 h per operand, the fp32 value of
-      // h times <= 4 cells, one FMA rounding; plus the fp64 rounding of the cell origins), so
+      // fp32 screening error: |offset error| <= E per axis (plus the fp64 rounding of the cell origins), so
       // |d2_fp32 - d2| <= 2 sqrt(3) E d + 3 E^2 + 4 * 2^-24 d2; the band is several times that at d = r
       double maxabs = 0;
       for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(c.bbox_min[a]), std::fabs(c.bbox_max[a])));
-      const double E = 1e-6 * c.lat.h + 4e-15 * maxabs;
+      // per axis: two fp32 representations (2 x 3e-8 h), their difference (3e-8 h), fl32(h) times up to R+1 cells and the
+      // FMA rounding (3e-8 h (2R + 3)) -> 3e-8 h (2R + 6); taken with a 3.3x margin
+      const double E = 1e-7 * (2.0 * rings + 6.0) * c.lat.h + 4e-15 * maxabs;
       const double band = 8.0 * radius * E + 12.0 * E * E + 1e-6 * C.r2;
       C.r2_lo = (float)((C.r2 - band) * (1.0 - 1e-7));
       C.r2_hi = (float)((C.r2 + band) * (1.0 + 1e-7));
@@ -337,7 +450,8 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
       C.dimx = c.lat.dims[0]; C.dimy = c.lat.dims[1]; C.dimz = c.lat.dims[2];
       if (rings == 1) ME_TRY(launch_flat<1>(ctx, c, qb, qe, C, acc));
       else if (rings == 2) ME_TRY(launch_flat<2>(ctx, c, qb, qe, C, acc));
-      else ME_TRY(launch_flat<3>(ctx, c, qb, qe, C, acc));
+      else if (rings == 3) ME_TRY(launch_flat<3>(ctx, c, qb, qe, C, acc));
+      else ME_TRY(launch_plane(ctx, c, qb, qe, C, rings, acc));
     } else {
       const int blocks = (int)std::min<long long>((qe - qb + kThreads - 1) / kThreads, (long long)ctx->sm_count * 64);
       mme_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, qb, qe, c.d_cell_off, c.lat, radius * radius, rc2, rings,
@@ -354,11 +468,24 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   out->min_entropy = dec_ordered(h->min_enc);
   out->max_entropy = dec_ordered(h->max_enc);
   c.entropy_valid = true;
+  c.entropy_caller_valid = false;
+  if (c.grid_solo) {      // the solo lattice (and with it the sorted order of d_entropy) does not survive the next build
+    ME_TRY(ensure(ctx, (void **)&c.d_entropy_caller, &c.cap_entropy_caller, c.n, sizeof(double)));
+    const int blocks = (int)std::min<long long>((c.n + 255) / 256, (long long)ctx->sm_count * 16);
+    unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.n, c.d_entropy, c.d_entropy_caller);
+    ME_LAUNCH_CHECK(ctx);
+    c.entropy_caller_valid = true;
+  }
   return ME_OK;
 }
 
 int unsort_entropy(me_ctx *ctx, int which, double *h_entropy) {
   Cloud &c = ctx->cloud[which];
+  if (c.entropy_caller_valid) {
+    ME_CUDA(ctx, cudaMemcpyAsync(h_entropy, c.d_entropy_caller, (size_t)c.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ME_OK;
+  }
   if (!c.entropy_valid) return fail(ctx, ME_ERR_INVALID, "me_get_entropies before me_eval_mme");
   ME_TRY(ensure_work(ctx, (size_t)c.n * sizeof(double)));
   double *dst = (double *)ctx->d_work;

@@ -156,18 +156,31 @@ def test_mme_parity(api, O, min_neighbors):
     np.testing.assert_allclose(got.max_abs_entropy, exp.max_abs_entropy, rtol=RTOL_ENT)
 
 
-@pytest.mark.parametrize("cells_per_radius", [1.0, 1.7, 2.6, 4.5])
-def test_mme_radius_to_cell_ratios(api, O, cells_per_radius):
-    """rings = 1, 2, 3 take the flat kernel (templated on the ring count), 5 rings the generic row walk."""
+@pytest.mark.parametrize("shared_lattice", [True, False])
+@pytest.mark.parametrize("cells_per_radius", [1.0, 1.7, 2.6, 4.5, 11.3, 19.0])
+def test_mme_radius_to_cell_ratios(api, O, cells_per_radius, shared_lattice):
+    """On the shared lattice rings = 1, 2, 3 take the flat kernel (templated on the ring count), 5 and 12 rings the plane
+    kernel, 19 rings the generic fp64 row walk.  By default a radius spanning more than 3 cells makes the sweep lay the
+    cloud out on a lattice of its own (h = r/2); the NN sweep afterwards goes back to the shared lattice."""
+    import os
     est, gt, cfg = synth.make_pair("C2", scale=0.05)
     r = cfg["nn_radius"]
-    with _ctx(api, est, gt, nn_cell_size=r / cells_per_radius) as ctx:
-        got, ent = ctx.computeMME(A.ME_CLOUD_EST, r, 10, want_entropies=True)
+    p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+    if shared_lattice:
+        os.environ["ME_MME_SHARED_LATTICE"] = "1"
+    try:
+        with _ctx(api, est, gt, nn_cell_size=r / cells_per_radius) as ctx:
+            got = ctx.computeMME(A.ME_CLOUD_EST, r, 10)
+            nn = ctx.calculateMetricsWithInitialMatrix(p)
+            ent = ctx.get_entropies(A.ME_CLOUD_EST)       # after the NN stage re-laid the cloud out
+    finally:
+        os.environ.pop("ME_MME_SHARED_LATTICE", None)
     exp, oent = O.eval_mme(est, r, 10, want_entropies=True)
     assert got.n_valid == exp.n_valid
     np.testing.assert_array_equal(ent != 0, oent != 0)
     np.testing.assert_allclose(ent, oent, rtol=RTOL_ENT, atol=0)
     np.testing.assert_allclose(got.mme, exp.mme, rtol=RTOL_MME)
+    _cmp_nn(nn, O.eval_nn(est, gt, p))
 
 
 def test_mme_neighbours_exactly_on_the_radius(api, O):
