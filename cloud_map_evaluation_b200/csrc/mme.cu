@@ -373,11 +373,9 @@ static int launch_flat(me_ctx *ctx, Cloud &c, long long qb, long long qe, const 
   constexpr int U2 = 1;
   constexpr int NROW = (2 * R + 1) * (2 * R + 1);
   const size_t smem = (size_t)NROW * kFlatThreads * RunTab<E16>::kEntryBytes;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // per launch (function attributes are per device; a process may drive several devices through several contexts)
+  if (smem > 48 * 1024)
     ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
   // fine-grained grid (~2 queries per thread): 64 CTAs/SM -> 4.83 ms, 256 -> 4.62 ms, 1024 -> 4.67 ms
   const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 256);
   mme_flat_kernel<R, E16, U2><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, c.d_entropy, acc);

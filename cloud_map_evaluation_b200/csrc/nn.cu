@@ -687,12 +687,9 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     fill_i32_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_nn_idx, Qc.n, -2);
     ME_LAUNCH_CHECK(ctx);
   }
-  static bool attr_done = false;
   const size_t dyn_smem = (size_t)kNNCap * (sizeof(P4) + sizeof(float4));
-  if (!attr_done) {
+  if (use_tile)      // per launch: function attributes are per device
     ME_CUDA(ctx, cudaFuncSetAttribute(nn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    attr_done = true;
-  }
   if (use_tile ? te > tb : qe > qb) {
     if (use_tile) {
       // persistent CTAs: each walks tiles tb + blockIdx.x, + gridDim.x, ... and flushes its accumulators once
