@@ -187,7 +187,8 @@ __device__ __forceinline__ float gap2(int d, float u) {
 }
 
 template <int R, bool E16, int U2>      // U2: 0 plain walk, 1 two candidates (two loads in flight) per iteration
-__global__ void __launch_bounds__(kFlatThreads)
+// 8 CTAs/SM at R <= 2 (64 registers, two spilled doubles): 4.62 -> 4.44 ms on C3; at R = 3 the 49-row table bounds it at 4
+__global__ void __launch_bounds__(kFlatThreads, (R <= 2 ? 8 : 4))
 mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
                 const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
                 MmeAcc *__restrict__ acc) {
