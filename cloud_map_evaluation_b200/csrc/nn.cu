@@ -390,7 +390,8 @@ struct FlatGeom {
 };
 
 template <bool E16, int U2>      // U2: 0 plain walk, 1 two candidates (two loads in flight) per iteration
-__global__ void __launch_bounds__(kFlatThreads)
+// 8 CTAs/SM: 1.38 / 1.76 ms on C3; 10: 1.47 / 1.85; 12: 1.56 / 1.95 (spills + less L1)
+__global__ void __launch_bounds__(kFlatThreads, 8)
 nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
                const P4 *__restrict__ R, const float4 *__restrict__ rrel, const uint32_t *__restrict__ r_off,
                Lattice Lr, FlatGeom G, NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
