@@ -293,7 +293,8 @@ def main():
                        "n_gt": n_gt, "tau": cfg["tau"], "icp_max_distance": 1.0, "nn_radius": cfg["nn_radius"],
                        "vmd_voxel_size": cfg["vmd_voxel_size"], "mme_gt": bool(cfg["gt_mme"]),
                        "parallelism": f"query-range shard x{world}, lattices replicated",
-                       "l2": "inputs (2 x 240 MB fp64 + 2 x 320 MB sorted) exceed the 126 MB L2; no flush needed"},
+                       "l2": "inputs per pass (2 x 240 MB fp64 clouds, 2 x 320 MB sorted records, 2 x 160 MB fp32 screening copies) "
+                             "exceed the 126 MB L2 several times over; no flush needed"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 24 * (n_est + n_gt),
                     "d2h_bytes_per_step": 2 * C.sizeof(A.me_nn_accum) + C.sizeof(A.me_mme_accum) * len(results["mme"])
