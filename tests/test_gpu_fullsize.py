@@ -1,0 +1,95 @@
+"""Full-size (BASELINE.json C3: 10 M vs 10 M points) checks through size-independent properties — the CPU oracle cannot
+run these sizes in test time, so the CUDA path is checked against itself under transformations that must not change the
+answer, and against brute force on a random sample of queries."""
+import numpy as np
+import pytest
+
+from cloud_map_evaluation_b200 import _abi as A
+from cloud_map_evaluation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from cloud_map_evaluation_b200 import api as _api
+    return _api
+
+
+@pytest.fixture(scope="module")
+def c3():
+    est, gt, cfg = synth.make_pair("C3")
+    assert len(est) == 10_000_000 and len(gt) == 10_000_000
+    return est, gt, cfg
+
+
+def _full_pass(api, est, gt, cfg, p, **kw):
+    with api.MapEvalB200(vmd_voxel_size=cfg["vmd_voxel_size"], **kw) as ctx:
+        ctx.set_cloud(A.ME_CLOUD_EST, est)
+        ctx.set_cloud(A.ME_CLOUD_GT, gt)
+        m = ctx.eval_mme_accum(A.ME_CLOUD_EST, cfg["nn_radius"], 10)
+        e, g = ctx.eval_nn_accum(p)
+        awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5)
+        nn_idx, nn_d2 = ctx.get_nn(A.ME_CLOUD_EST) if kw.get("world", 1) == 1 else (None, None)
+    return m, e, g, awd, nn_idx, nn_d2
+
+
+def _ints(a):
+    return [a.n_query, a.n_corr] + list(a.n_inlier) + [a.n_ub]
+
+
+def test_c3_full_size_properties(api, c3):
+    est, gt, cfg = c3
+    p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+    m0, e0, g0, a0, idx0, d20 = _full_pass(api, est, gt, cfg, p)
+    assert e0.n_query == len(est) and g0.n_query == len(gt) and m0.n_query == len(est)
+    assert e0.n_inlier[0] >= e0.n_inlier[1] >= e0.n_inlier[4] > 0          # thresholds are nested
+    assert 0 < m0.n_valid <= len(est) and a0.n_pairs > 1000
+
+    # 1. idempotence: a second pass gives bit-identical integers (fp sums differ by the atomics' order only)
+    m1, e1, g1, a1, _, _ = _full_pass(api, est, gt, cfg, p)
+    assert _ints(e1) == _ints(e0) and _ints(g1) == _ints(g0) and m1.n_valid == m0.n_valid and a1.n_pairs == a0.n_pairs
+    np.testing.assert_allclose([e1.sum_d2_all, g1.sum_nn_dist, m1.sum_entropy, a1.awd, a1.scs],
+                               [e0.sum_d2_all, g0.sum_nn_dist, m0.sum_entropy, a0.awd, a0.scs], rtol=1e-12)
+
+    # 2. permutation invariance: the metrics do not depend on the order of the points
+    perm = np.random.RandomState(1).permutation(len(est))
+    m2, e2, g2, a2, idx2, d22 = _full_pass(api, est[perm], gt, cfg, p)
+    assert _ints(e2) == _ints(e0) and _ints(g2) == _ints(g0) and m2.n_valid == m0.n_valid and a2.n_pairs == a0.n_pairs
+    np.testing.assert_allclose([e2.sum_d2_all, e2.sum_nn_dist, g2.sum_nn_dist, m2.sum_entropy, a2.awd, a2.scs],
+                               [e0.sum_d2_all, e0.sum_nn_dist, g0.sum_nn_dist, m0.sum_entropy, a0.awd, a0.scs], rtol=1e-11)
+    np.testing.assert_array_equal(d22, d20[perm])                            # per-point NN distances move with the points
+    np.testing.assert_array_equal(idx2, idx0[perm])
+
+    # 3. shard invariance: two ranks (one context each) sum to the single-context result
+    tot = None
+    for r in range(2):
+        m, e, g, _, _, _ = _full_pass(api, est, gt, cfg, p, rank=r, world=2)
+        part = np.array(_ints(e) + _ints(g) + [m.n_query, m.n_valid], dtype=np.int64)
+        fl = np.array([e.sum_d2_all, e.sum_nn_dist, g.sum_d2_all, g.sum_nn_dist, m.sum_entropy])
+        tot = (part, fl) if tot is None else (tot[0] + part, tot[1] + fl)
+    assert list(tot[0]) == _ints(e0) + _ints(g0) + [m0.n_query, m0.n_valid]
+    np.testing.assert_allclose(tot[1], [e0.sum_d2_all, e0.sum_nn_dist, g0.sum_d2_all, g0.sum_nn_dist, m0.sum_entropy], rtol=1e-12)
+
+    # 4. translation by a large power-of-two vector (the clouds hold fp32 values, so x + 4096 is exact in fp64 except for
+    #    the handful of coordinates below ~4e-6): the same distances, hence the same integer results, while the lattice,
+    #    the cell-relative fp32 copies and every float sum are different objects now
+    shift = np.array([4096.0, -8192.0, 2048.0])
+    es, gs = est + shift, gt + shift
+    m3, e3, g3, a3, _, d23 = _full_pass(api, es, gs, cfg, p)
+    assert _ints(e3) == _ints(e0) and _ints(g3) == _ints(g0) and m3.n_valid == m0.n_valid
+    exact = ((es - shift) == est).all(axis=1)
+    assert exact.mean() > 0.9999
+    np.testing.assert_allclose(d23, d20, rtol=1e-9)
+    assert (d23[exact] != d20[exact]).mean() < 1e-5       # a query is also affected when its neighbour moved inexactly
+    np.testing.assert_allclose(m3.sum_entropy, m0.sum_entropy, rtol=1e-7)
+
+    # 5. brute force on a random sample of queries (fp64, the reference's operation order)
+    rs = np.random.RandomState(7)
+    sample = rs.choice(len(est), 64, replace=False)
+    for i in sample:
+        d = est[i] - gt
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        j = int(np.argmin(d2))
+        assert d20[i] == d2[j] and (idx0[i] == j or d2[idx0[i]] == d2[j])
+    # ... and of MME neighbour counts through the validity flags of far-from-typical points is covered at small size
