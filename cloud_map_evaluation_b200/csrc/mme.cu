@@ -11,12 +11,16 @@
 // the query is its own nearest neighbour at d = 0 and contributes nothing, which is exactly the reference's
 // "erase the first hit" (:1672-1673), and cov = (S2 - S1 S1^T / k) / (k - 1) equals the reference's centred product.
 //
-// One thread per query, queries walked in cell-sorted order.  Rows of the (2k+1)^2 neighbourhood are pruned by their y/z distance and their
-// x-extent trimmed to the chord of the sphere; every candidate is tested in fp64 with the reference's operation
-// order (d2 < r*r, strict).  A shared-memory staged variant (TMA bulk copies + fp32 screening, as the NN sweep uses)
-// was measured SLOWER here (9.9 ms vs 6.5 ms on 10 M points, profiles/r01_mme_tile_experiment.txt): with ~50 accepted
-// neighbours per query the accept path needs the exact fp64 record of nearly every candidate, so the shared-memory
-// pipe (random 32-byte reads, bank conflicts) becomes the limiter instead of L1.
+// Kernels, all one thread per query with the queries in cell-sorted order (a warp = x-neighbours of one lattice row):
+//   mme_flat_kernel<R>  (R = ceil(r/h) <= 3, the dominant kernel of the pass): per-thread run table in shared memory,
+//                       flattened candidate walk, fp32 screening on the cell-relative copy, exact fp64 decision inside
+//                       the fp32 error band (the neighbour COUNT is bit-exact), fp64 moment accumulation.
+//   mme_plane_kernel    (4..15 rings): the same walk with a run table of one dz plane at a time.
+//   mme_kernel          (> 15 rings): nested row walk with fp64 tests on the 32-byte records.
+// run_mme picks the lattice per radius: when the radius spans more than 3 cells of the shared lattice the cloud is laid
+// out on a lattice of its own with h = r/2 for this sweep.  Variants that were measured and dropped (shared-memory
+// tile + TMA staging, 16-byte table entries, software prefetch, plane tables at R = 2): profiles/r01_kernel_variants.md.
+// Test hooks (environment): ME_MME_WALK forces mme_kernel, ME_MME_SHARED_LATTICE keeps the shared lattice.
 #include "common.cuh"
 #include "flat.cuh"
 #include <algorithm>

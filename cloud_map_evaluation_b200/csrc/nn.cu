@@ -1,4 +1,4 @@
-// nn.cu — exact 1-NN sweeps with fused inlier accumulators.
+// nn.cu — exact 1-NN sweeps and the inlier statistics built on them.
 //
 // Replaces (reference, map_eval/src/map_eval.cpp):
 //   :1213-1236  two serial KDTreeFlann::SearchKNN(p, 1) loops of calculateMetricsWithInitialMatrix
@@ -7,11 +7,16 @@
 //
 // One thread per query, queries walked in their own cell-sorted order so that a warp's 32 queries sit in the same
 // few lattice rows and its candidate loads hit the same L1 lines.  Per query the 3x3x3 cell block of the reference
-// lattice is read as 9 contiguous x-runs (3 x-adjacent cells are adjacent in the CSR layout).  All candidate
-// distances are evaluated in fp64 with exactly the reference's operation order (no FMA contraction), so the
-// arg-min, the cut-off test and every inlier comparison are bit-identical to the CPU path.  A query whose best
-// distance does not beat the distance to the faces of its searched block is finished by a warp-per-query
-// ring-expansion kernel (rare: ~0.1 % of queries on volume-filling clouds).
+// lattice is 9 contiguous x-runs (3 x-adjacent cells are adjacent in the CSR layout).  Candidates are screened in fp32
+// on the cell-relative copies; the winner — and every candidate inside the fp32 error bound of the winner — is evaluated
+// in fp64 with exactly the reference's operation order (no FMA contraction), so the arg-min, the cut-off test and every
+// inlier comparison are bit-identical to the CPU path.  A query whose best distance does not beat the distance to the
+// faces of its searched block is finished by a warp-per-query ring-expansion kernel (rare: ~0.05 % of queries on
+// volume-filling clouds).  The sweeps only record (index, nanoflann-order d2, Eigen-order squared norm) per query;
+// nn_stats_kernel folds those arrays into the accumulators.
+//   nn_flat_kernel   default: per-thread run table in shared memory + flattened candidate walk
+//   nn_tile_kernel   lattices the flat kernel cannot index (>= 2^24 cells along x or points per run): one CTA per
+//                    4x4x4-cell query tile, 6x6x6-cell region staged with TMA bulk copies.  ME_NN_TILE (env) forces it.
 #include "common.cuh"
 #include "tile.cuh"
 #include "flat.cuh"
