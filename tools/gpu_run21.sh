@@ -1,0 +1,6 @@
+for pf in 0 1; do
+  touch cloud_map_evaluation_b200/csrc/nn.cu cloud_map_evaluation_b200/csrc/mme.cu
+  if [ $pf = 1 ]; then X="-DME_RUN_PREFETCH"; else X=""; fi
+  make -s -C cloud_map_evaluation_b200/csrc EXTRA="$X" 2>&1 | grep -E " error"
+  echo "run prefetch $pf"; python tools/ab_kernels.py C3 "" 2>&1 | tail -1
+done | tee gpurun_out/ab21.log
