@@ -415,3 +415,44 @@ def test_voxel_downsample_errors(api):
         with pytest.raises(api.MapEvalError):
             ctx.voxel_downsample(A.ME_CLOUD_EST, 1e-7)             # more than 2^21 voxels per axis
         assert ctx.voxel_downsample(A.ME_CLOUD_EST, 100.0) == 1    # everything in one voxel
+
+
+def test_tiny_and_degenerate_clouds(api, O):
+    """Ragged / degenerate inputs: single points, a handful of points, all points identical, collinear points, clouds of
+    very different extent.  The reference's own guards: empty clouds end process() (map_eval.cpp:32-35); 0/0 -> NaN for
+    AWD / SCS without voxel pairs (:324, :387); MME without valid points returns 0 (:1720-1724)."""
+    p = A.make_nn_params([0.2, 0.1, 0.08, 0.05, 0.01], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+    rng = np.random.RandomState(3)
+    cases = {
+        "one_vs_one": (np.array([[0.1, 0.2, 0.3]]), np.array([[0.1, 0.2, 0.35]])),
+        "one_vs_many": (np.array([[0.5, 0.5, 0.5]]), rng.rand(300, 3)),
+        "few": (rng.rand(7, 3), rng.rand(5, 3)),
+        "identical_points": (np.tile([[1.0, 2.0, 3.0]], (200, 1)), np.tile([[1.0, 2.0, 3.01]], (150, 1))),
+        "collinear": (np.stack([np.linspace(0, 1, 400), np.zeros(400), np.zeros(400)], 1),
+                      np.stack([np.linspace(0, 1, 300), np.full(300, 0.02), np.zeros(300)], 1)),
+        "disjoint_extents": (rng.rand(500, 3) * 0.5, rng.rand(400, 3) * 0.5 + np.array([40.0, -3.0, 7.0])),
+    }
+    for name, (est, gt) in cases.items():
+        est, gt = np.ascontiguousarray(est, dtype=np.float64), np.ascontiguousarray(gt, dtype=np.float64)
+        with _ctx(api, est, gt) as ctx:
+            nn = ctx.calculateMetricsWithInitialMatrix(p)
+            mme, ent = ctx.computeMME(A.ME_CLOUD_EST, 0.1, 10, want_entropies=True)
+            awd = ctx.calculateVMD(0.25, 100, 5)
+        _cmp_nn(nn, O.eval_nn(est, gt, p))
+        omme, oent = O.eval_mme(est, 0.1, 10, want_entropies=True)
+        assert (mme.n_valid, mme.n_total) == (omme.n_valid, omme.n_total), name
+        np.testing.assert_array_equal(ent != 0, oent != 0, err_msg=name)
+        ok = oent > -25                      # (near-)singular neighbourhoods: det is a rounding-noise quantity
+        np.testing.assert_allclose(ent[ok], oent[ok], rtol=1e-5, err_msg=name)
+        oawd = O.eval_awd(est, gt, 0.25, 100, 5)
+        assert (awd.n_pairs, awd.n_scs, awd.n_voxels_est, awd.n_voxels_gt) == \
+               (oawd.n_pairs, oawd.n_scs, oawd.n_voxels_est, oawd.n_voxels_gt), name
+        np.testing.assert_allclose([awd.awd, awd.scs], [oawd.awd, oawd.scs], rtol=1e-9, equal_nan=True, err_msg=name)
+    # empty clouds are refused (map_eval.cpp:32-35)
+    with api.MapEvalB200() as ctx:
+        ctx.set_cloud(A.ME_CLOUD_EST, np.zeros((0, 3)))
+        ctx.set_cloud(A.ME_CLOUD_GT, rng.rand(10, 3))
+        with pytest.raises(api.MapEvalError):
+            ctx.calculateMetricsWithInitialMatrix(p)
+        with pytest.raises(api.MapEvalError):
+            ctx.computeMME(A.ME_CLOUD_EST, 0.1, 10)
