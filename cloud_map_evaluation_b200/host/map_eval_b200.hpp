@@ -32,6 +32,7 @@
 
 #include "../../include/mapeval_b200.h"
 #include "cloud_io.hpp"
+#include "gpu_group.hpp"
 #include "yaml_lite.hpp"
 
 namespace fs = std::filesystem;
@@ -62,6 +63,7 @@ struct Param {   // map_eval.h:60-116
   double downsample_size = 0.01;
   // additions of this implementation (absent keys keep the reference behaviour)
   int gpu_device_ = 0;
+  int n_gpus_ = 1;                      // GPUs gpu_device_ .. gpu_device_ + n_gpus_ - 1 share the sweeps (NCCL all-reduce)
   bool geometric_gt_pairing_ = false;   // false = reproduce map_eval.cpp:1233/:1241 verbatim
 };
 
@@ -101,6 +103,7 @@ inline Param loadParametersFromYAML(const std::string &yaml_file_path) {
     param.enable_debug = config["enable_debug"].as<bool>();
     if (config["use_tbb_mme"]) param.use_tbb_mme = config["use_tbb_mme"].as<bool>();
     if (config["gpu_device"]) param.gpu_device_ = config["gpu_device"].as<int>();
+    if (config["n_gpus"]) param.n_gpus_ = config["n_gpus"].as<int>();
     if (config["geometric_gt_pairing"]) param.geometric_gt_pairing_ = config["geometric_gt_pairing"].as<bool>();
     return param;
   } catch (const std::exception &e) {
@@ -180,7 +183,7 @@ class MapEvalB200 {
   }
   ~MapEvalB200() {
     file_result.close();
-    if (ctx_) me_destroy(ctx_);
+    gpus_.destroy();
   }
 
   int process();                                   // map_eval.cpp:4-102
@@ -200,10 +203,12 @@ class MapEvalB200 {
 
  private:
   int fail(const char *what) {
-    std::cerr << "ERROR: " << what << ": " << (ctx_ ? me_last_error(ctx_) : me_last_error(nullptr)) << std::endl;
+    std::cerr << "ERROR: " << what << ": "
+              << (!gpus_.error().empty() ? gpus_.error().c_str() : (ctx_ ? me_last_error(ctx_) : me_last_error(nullptr))) << std::endl;
     return -1;
   }
-  me_ctx *ctx_ = nullptr;
+  GpuGroup gpus_;            // one context per GPU; rank r evaluates the r-th shard of every sweep's query range
+  me_ctx *ctx_ = nullptr;    // = gpus_.ctx(0): the voxel stage and the single-GPU calls
   std::vector<double> map_3d_, gt_3d_;   // N x 3 fp64, the layout of open3d PointCloud::points_ (as loaded)
   int64_t n_est_ = 0, n_gt_ = 0;         // point counts after VoxelDownSample (the clouds the metrics see)
   double t1, t2, t3, t4, t5, t6, t7, t_fcd = 0.0, t_acc = 0.0;
@@ -235,24 +240,24 @@ inline int MapEvalB200::process() {
     std::cerr << "ERROR: One or both point clouds are empty!" << std::endl;
     return -1;
   }
-  me_options opt{};
-  opt.abi_version = ME_ABI_VERSION;
-  opt.device = param_.gpu_device_;
-  opt.rank = 0; opt.world = 1;
-  opt.vmd_voxel_size = param_.vmd_voxel_size_;
-  if (me_create(&opt, &ctx_) != ME_OK) return fail("cannot create the B200 context");
-  if (me_set_cloud(ctx_, ME_CLOUD_EST, map_3d_.data(), (int64_t)(map_3d_.size() / 3)) != ME_OK) return fail("me_set_cloud(est)");
-  if (me_set_cloud(ctx_, ME_CLOUD_GT, gt_3d_.data(), (int64_t)(gt_3d_.size() / 3)) != ME_OK) return fail("me_set_cloud(gt)");
-
-  // map_3d_ = map_3d_->VoxelDownSample(param_.downsample_size); gt_3d_ likewise (map_eval.cpp:38-39), on the GPU.
+  if (!gpus_.create(std::max(1, param_.n_gpus_), param_.gpu_device_, param_.vmd_voxel_size_)) return fail("cannot create the B200 context(s)");
+  ctx_ = gpus_.ctx(0);
+  if (gpus_.size() > 1) std::cout << "INFO: sharding the sweeps over " << gpus_.size() << " GPUs (NCCL all-reduce of the accumulators)" << std::endl;
+  // every GPU holds both clouds (the lattices are replicated); VoxelDownSample (map_eval.cpp:38-39) runs on each of them.
   // The reference calls it unconditionally (Open3D raises for voxel_size <= 0); a non-positive value skips the step here.
-  int64_t n_est = (int64_t)(map_3d_.size() / 3), n_gt = (int64_t)(gt_3d_.size() / 3);
-  if (param_.downsample_size > 0) {
-    if (me_voxel_downsample(ctx_, ME_CLOUD_EST, param_.downsample_size, &n_est) != ME_OK) return fail("me_voxel_downsample(est)");
-    if (me_voxel_downsample(ctx_, ME_CLOUD_GT, param_.downsample_size, &n_gt) != ME_OK) return fail("me_voxel_downsample(gt)");
-  } else {
-    std::cout << "INFO: downsample_size <= 0: clouds are evaluated as loaded." << std::endl;
-  }
+  std::vector<int64_t> ne(gpus_.size(), (int64_t)(map_3d_.size() / 3)), ng(gpus_.size(), (int64_t)(gt_3d_.size() / 3));
+  if (gpus_.for_each([&](int r, me_ctx *c) {
+        int rc = me_set_cloud(c, ME_CLOUD_EST, map_3d_.data(), (int64_t)(map_3d_.size() / 3));
+        if (rc == ME_OK) rc = me_set_cloud(c, ME_CLOUD_GT, gt_3d_.data(), (int64_t)(gt_3d_.size() / 3));
+        if (rc == ME_OK && param_.downsample_size > 0) {
+          rc = me_voxel_downsample(c, ME_CLOUD_EST, param_.downsample_size, &ne[r]);
+          if (rc == ME_OK) rc = me_voxel_downsample(c, ME_CLOUD_GT, param_.downsample_size, &ng[r]);
+        }
+        return rc;
+      }) != ME_OK)
+    return fail("uploading / down-sampling the clouds");
+  if (!(param_.downsample_size > 0)) std::cout << "INFO: downsample_size <= 0: clouds are evaluated as loaded." << std::endl;
+  const int64_t n_est = ne[0], n_gt = ng[0];
   n_est_ = n_est; n_gt_ = n_gt;
 
   file_result << std::fixed << std::setprecision(15) << "Estimated-Ground Truth point count: " << n_est << " / " << n_gt
@@ -293,13 +298,20 @@ inline int MapEvalB200::process() {
 inline int MapEvalB200::computeMME() {
   if (!param_.evaluate_mme_) return 0;
   // use_tbb_mme only selects between two CPU threadings of the same arithmetic in the reference (:153-157)
-  if (me_eval_mme(ctx_, ME_CLOUD_EST, param_.nn_radius_, 10, &mme_est_res_, nullptr) != ME_OK) return fail("me_eval_mme(est)");
+  auto eval_mme = [&](int which, int min_neighbors, int64_t n_total, me_mme_result *out) -> int {
+    std::vector<me_mme_accum> acc(gpus_.size());
+    if (gpus_.for_each([&](int r, me_ctx *c) { return me_eval_mme_accum(c, which, param_.nn_radius_, min_neighbors, &acc[r]); }) != ME_OK)
+      return -1;
+    if (!gpus_.reduce_mme(acc)) return -1;
+    return me_mme_finalize(&acc[0], n_total, out) == ME_OK ? 0 : -1;
+  };
+  if (eval_mme(ME_CLOUD_EST, 10, n_est_, &mme_est_res_) != 0) return fail("me_eval_mme(est)");
   mme_est = mme_est_res_.mme;
   if (mme_est_res_.n_valid * 100.0 / (double)mme_est_res_.n_total < 0.6)
     std::cerr << "valid points is too small, please check the input point cloud" << std::endl;   // :1732
   min_abs_entropy = mme_est_res_.min_abs_entropy; max_abs_entropy = mme_est_res_.max_abs_entropy;   // :179 -> :700-701
   if (param_.evaluate_gt_mme_) {
-    if (me_eval_mme(ctx_, ME_CLOUD_GT, param_.nn_radius_, 5, &mme_gt_res_, nullptr) != ME_OK) return fail("me_eval_mme(gt)");
+    if (eval_mme(ME_CLOUD_GT, 5, n_gt_, &mme_gt_res_) != 0) return fail("me_eval_mme(gt)");
     mme_gt = mme_gt_res_.mme;
     std::cout << "GT MME Valid_points " << mme_gt_res_.n_valid * 100.0 / (double)mme_gt_res_.n_total << "% " << mme_gt_res_.n_valid
               << " " << mme_gt_res_.n_total << std::endl;
@@ -316,7 +328,6 @@ inline int MapEvalB200::calculateMetricsWithInitialMatrix() {
   if (!param_.trunc_dist_set_)
     std::cerr << "WARNING: accuracy_level missing: the reference would read an uninitialised trunc_dist_ (map_eval.h:85); using zeros."
               << std::endl;
-  if (me_transform(ctx_, ME_CLOUD_EST, param_.initial_matrix_) != ME_OK) return fail("me_transform");
   me_nn_params p{};
   for (int i = 0; i < 5; ++i) p.tau[i] = param_.trunc_dist_[i];
   p.icp_max_distance = param_.icp_max_distance_;
@@ -326,7 +337,14 @@ inline int MapEvalB200::calculateMetricsWithInitialMatrix() {
   // so they are produced and reported on stdout, while the results file keeps the reference's value
   p.want_full_cd = 1;
   p.directions = 3;
-  if (me_eval_nn(ctx_, &p, &nn_) != ME_OK) return fail("me_eval_nn");
+  std::vector<me_nn_accum> e2g(gpus_.size()), g2e(gpus_.size());
+  if (gpus_.for_each([&](int r, me_ctx *c) {
+        int rc = me_transform(c, ME_CLOUD_EST, param_.initial_matrix_);      // map_3d_->Transform(initial_matrix), :1206
+        return rc != ME_OK ? rc : me_eval_nn_accum(c, &p, &e2g[r], &g2e[r]);
+      }) != ME_OK)
+    return fail("me_transform / me_eval_nn_accum");
+  if (!gpus_.reduce_nn(e2g, g2e)) return fail("all-reduce of the NN accumulators");
+  if (me_nn_finalize(&p, &e2g[0], &g2e[0], n_est_, n_gt_, &nn_) != ME_OK) return fail("me_nn_finalize");
   t_acc = tic.toc() / 1000.0;
   std::cout << "INFO: Chamfer Distance: " << eigenRow(nn_.cd, 5, 6) << std::endl;
   std::cout << "INFO: F1 Score: " << eigenRow(nn_.f1, 5, 6) << std::endl;

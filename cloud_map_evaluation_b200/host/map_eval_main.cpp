@@ -1,6 +1,6 @@
 // map_eval — the re-hosted MapEval executable (reference: map_eval/src/map_eval_main.cpp:211-244).
 //
-//   map_eval [config.yaml] [--dump-config] [--read-cloud file.pcd|file.ply]
+//   map_eval [config.yaml] [--gpus N] [--dump-config] [--read-cloud file.pcd|file.ply]
 //
 // Without an argument the configuration is read from ../config/config.yaml relative to the working directory, the
 // reference's hard-coded path (map_eval_main.cpp:213; its argv handling is commented out at :214-216).
@@ -28,6 +28,7 @@ static void displayProgramInformation(const Param &param) {
 int main(int argc, char **argv) {
   std::string config_file = "../config/config.yaml";
   bool dump = false;
+  int gpus_override = 0;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--dump-config") dump = true;
@@ -43,7 +44,8 @@ int main(int argc, char **argv) {
       for (size_t k = 0; k + 2 < xyz.size(); k += 3) { sx += xyz[k]; sy += xyz[k + 1]; sz += xyz[k + 2]; }
       std::cout << std::setprecision(17) << "points " << xyz.size() / 3 << " sum " << sx << " " << sy << " " << sz << "\n";
       return EXIT_SUCCESS;
-    } else config_file = a;
+    } else if (a == "--gpus" && i + 1 < argc) gpus_override = std::atoi(argv[++i]);
+    else config_file = a;
   }
   std::cout << "Loading configuration from: " << config_file << "\n";
   Param param;
@@ -53,6 +55,7 @@ int main(int argc, char **argv) {
     std::cerr << "\n[ERROR] Failed to load configuration: " << e.what() << "\n";
     return EXIT_FAILURE;
   }
+  if (gpus_override > 0) param.n_gpus_ = gpus_override;
   if (dump) {
     dumpParam(param, std::cout);
     return EXIT_SUCCESS;

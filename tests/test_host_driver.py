@@ -225,3 +225,35 @@ def test_map_eval_with_downsampling(exe, tmp_path):
     assert abs(float(line["MME"][0]) - me.mme) < 6e-6
     oawd = O.eval_awd(de, dg, 0.25, 100, 5)
     assert abs(float(line["VMD"][0]) - oawd.awd) < 6e-6 and abs(float(line["SCS"][0]) - oawd.scs) < 6e-6
+
+
+@pytest.mark.gpu
+def test_map_eval_two_gpus_matches_one(exe, tmp_path):
+    """`map_eval --gpus 2`: one context per GPU in one process, the sweeps' query ranges sharded, the accumulators
+    combined with an NCCL all-reduce in the C++ driver (gpu_group.hpp).  Same result lines as the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cloud_map_evaluation_b200 import synth
+    est, gt, cfg = synth.make_pair("C2", scale=0.3)
+    outs = {}
+    for n in (1, 2):
+        d = tmp_path / f"run{n}"
+        est_dir = d / "est"
+        est_dir.mkdir(parents=True)
+        _write_pcd(str(est_dir / "map.pcd"), est, "binary")
+        _write_pcd(str(d / "gt.pcd"), gt, "binary")
+        text = CONFIG.format(est=str(est_dir), gt=str(d / "gt.pcd"), gt_mme="true", initial="true")
+        text = text.replace("[1.0, 0.0, 0.0, 0.5]", "[1.0, 0.0, 0.0, 0.0]").replace("[0.0, 0.0, 1.0, -2]", "[0.0, 0.0, 1.0, 0.0]")
+        text = text.replace("downsample_size: 0.0", "downsample_size: 0.02")
+        (d / "config.yaml").write_text(text)
+        out = subprocess.run([exe, str(d / "config.yaml"), "--gpus", str(n)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+        res = (est_dir / "map_results" / "map_results.txt").read_text().splitlines()
+        outs[n] = {l.split(":")[0]: l.split(":", 1)[1].split() for l in res if ":" in l and not l.startswith(("Ground", "Evaluation"))}
+        if n == 2:
+            assert "sharding the sweeps over 2 GPUs" in out.stdout
+    for key in ("Estimated-Ground Truth point count", "Comp"):
+        assert outs[1][key] == outs[2][key], key
+    for key in ("RMSE/AC", "MME", "VMD", "SCS"):
+        np.testing.assert_allclose([float(x) for x in outs[2][key]], [float(x) for x in outs[1][key]], rtol=1e-12, atol=1e-12, err_msg=key)
