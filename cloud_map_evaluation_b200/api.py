@@ -186,6 +186,17 @@ class MapEvalB200:
         self._L.me_free(rows_p)
         return out, rows
 
+    def awd_from_rows(self, rows27, voxel_size, scs_radius=5):
+        """W per row + AWD / SCS from given voxel Gaussians (27-column voxel_errors.txt rows)."""
+        rows = np.ascontiguousarray(rows27, dtype=np.float64)
+        assert rows.ndim == 2 and rows.shape[1] == 27
+        out = A.me_awd_result()
+        w = np.empty(rows.shape[0], np.float64)
+        dp = C.POINTER(C.c_double)
+        self._check(self._L.me_awd_from_rows(self._ctx, rows.ctypes.data_as(dp), rows.shape[0], float(voxel_size), int(scs_radius),
+                                             w.ctypes.data_as(dp), C.byref(out)))
+        return out, w
+
     # -- introspection -----------------------------------------------------------------------------------------
     def stage_times_ms(self):
         ms = (C.c_double * A.ME_N_STAGE_TIMES)()

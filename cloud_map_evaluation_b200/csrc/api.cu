@@ -360,6 +360,13 @@ int me_eval_awd(me_ctx *ctx, double voxel_size, int32_t min_points, int32_t scs_
   return run_awd(ctx, voxel_size, min_points, scs_radius, out, n_rows, rows27);
 }
 
+int me_awd_from_rows(me_ctx *ctx, const double *rows27, int64_t n_rows, double voxel_size, int32_t scs_radius, double *w_out,
+                     me_awd_result *out) {
+  ME_ENTER(ctx);
+  if (!out) return fail(ctx, ME_ERR_INVALID, "null result");
+  return run_awd_rows(ctx, rows27, n_rows, voxel_size, scs_radius, w_out, out);
+}
+
 void me_free(void *p) { std::free(p); }
 
 int me_get_stage_times(me_ctx *ctx, double ms[ME_N_STAGE_TIMES]) {

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <climits>
 
 namespace me {
 
@@ -428,6 +429,90 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
     }
     *rows27 = hr;
   }
+  return ME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The voxel-pair stage on GIVEN voxel Gaussians: rows in the 27-column layout of voxel_errors.txt (map_eval.cpp:292-302).
+// Recomputes W with the device implementation of computeWassersteinDistanceGaussian and AWD / SCS over those voxels with
+// the production scs_kernel.  Lets the tests pin the kernels directly to the reference's shipped sample output.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+awd_rows_kernel(const double *__restrict__ rows, long long n, const long long *__restrict__ vox_of_row,
+                double *__restrict__ w_rows, double *__restrict__ w_vox, uint32_t *__restrict__ pair_list,
+                AwdAcc *__restrict__ acc) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double *r = rows + i * 27;
+    double mu_e[3] = {r[6], r[7], r[8]}, mu_g[3] = {r[18], r[19], r[20]}, sig_e[9], sig_g[9];
+    sig_e[0] = r[12]; sig_e[1] = r[13]; sig_e[2] = r[14]; sig_e[3] = r[13]; sig_e[4] = r[15]; sig_e[5] = r[16];
+    sig_e[6] = r[14]; sig_e[7] = r[16]; sig_e[8] = r[17];
+    sig_g[0] = r[21]; sig_g[1] = r[22]; sig_g[2] = r[23]; sig_g[3] = r[22]; sig_g[4] = r[24]; sig_g[5] = r[25];
+    sig_g[6] = r[23]; sig_g[7] = r[25]; sig_g[8] = r[26];
+    const double w = wasserstein(mu_g, sig_g, (int)r[10], mu_e, sig_e, (int)r[11]);    // (gt, est), map_eval.cpp:284
+    w_rows[i] = w;
+    w_vox[vox_of_row[i]] = w;
+    pair_list[i] = (uint32_t)vox_of_row[i];
+    atomicAdd(&acc->sum_w, w);
+    if (i == 0) acc->n_pairs = (unsigned long long)n;
+  }
+}
+__global__ void fill_nan_kernel(double *p, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = NAN;
+}
+
+int run_awd_rows(me_ctx *ctx, const double *rows27, int64_t n_rows, double voxel_size, int scs_radius, double *w_out,
+                 me_awd_result *out) {
+  std::memset(out, 0, sizeof(*out));
+  if (n_rows <= 0 || !rows27 || !(voxel_size > 0)) return fail(ctx, ME_ERR_INVALID, "bad arguments");
+  if (scs_radius < 0 || scs_radius > 64) return fail(ctx, ME_ERR_INVALID, "scs_radius out of range");
+  // voxel keys = vmin / v (columns 0-2), dense index inside their bounding box
+  std::vector<long long> key(3 * (size_t)n_rows), vox((size_t)n_rows);
+  long long lo[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX}, hi[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  for (int64_t i = 0; i < n_rows; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const long long k = llround(rows27[i * 27 + a] / voxel_size);
+      key[3 * i + a] = k; lo[a] = std::min(lo[a], k); hi[a] = std::max(hi[a], k);
+    }
+  Lattice L;
+  std::memset(&L, 0, sizeof(L));
+  long long nvox = 1;
+  for (int a = 0; a < 3; ++a) {
+    if (hi[a] - lo[a] + 1 > 4096) return fail(ctx, ME_ERR_RANGE, "voxel keys span too large a box");
+    L.nvox[a] = (int)(hi[a] - lo[a] + 1); nvox *= L.nvox[a];
+  }
+  L.nvoxels = nvox; L.v = voxel_size;
+  for (int64_t i = 0; i < n_rows; ++i)
+    vox[i] = ((key[3 * i + 2] - lo[2]) * L.nvox[1] + (key[3 * i + 1] - lo[1])) * L.nvox[0] + (key[3 * i] - lo[0]);
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_rows = 0, o_vox = o_rows + align((size_t)n_rows * 27 * 8), o_w = o_vox + align((size_t)n_rows * 8),
+               o_wv = o_w + align((size_t)n_rows * 8), o_pl = o_wv + align((size_t)nvox * 8), total = o_pl + align((size_t)n_rows * 4);
+  ME_TRY(ensure_work(ctx, total));
+  char *base = (char *)ctx->d_work;
+  double *d_rows = (double *)(base + o_rows), *d_w = (double *)(base + o_w), *d_wv = (double *)(base + o_wv);
+  long long *d_vox = (long long *)(base + o_vox);
+  uint32_t *d_pl = (uint32_t *)(base + o_pl);
+  AwdAcc *acc = (AwdAcc *)ctx->d_scratch;
+  unsigned long long *occ = (unsigned long long *)((char *)ctx->d_scratch + 256);
+  ME_CUDA(ctx, cudaMemcpyAsync(d_rows, rows27, (size_t)n_rows * 27 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ME_CUDA(ctx, cudaMemcpyAsync(d_vox, vox.data(), (size_t)n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+  zero_awd_acc_kernel<<<1, 1, 0, ctx->stream>>>(acc, occ);
+  ME_LAUNCH_CHECK(ctx);
+  fill_nan_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(d_wv, nvox);
+  ME_LAUNCH_CHECK(ctx);
+  awd_rows_kernel<<<std::max(1, (int)std::min<long long>((n_rows + kThreads - 1) / kThreads, ctx->sm_count * 8)), kThreads, 0, ctx->stream>>>(
+      d_rows, n_rows, d_vox, d_w, d_wv, d_pl, acc);
+  ME_LAUNCH_CHECK(ctx);
+  if (scs_radius == 5) scs_kernel<5><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(L, d_wv, d_pl, scs_radius, acc);
+  else scs_kernel<0><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(L, d_wv, d_pl, scs_radius, acc);
+  ME_LAUNCH_CHECK(ctx);
+  AwdAcc *h = (AwdAcc *)ctx->h_pinned;
+  ME_CUDA(ctx, cudaMemcpyAsync(h, acc, sizeof(AwdAcc), cudaMemcpyDeviceToHost, ctx->stream));
+  if (w_out) ME_CUDA(ctx, cudaMemcpyAsync(w_out, d_w, (size_t)n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out->n_pairs = n_rows;
+  out->n_scs = (int64_t)h->n_scs;
+  out->awd = h->sum_w / (double)n_rows;
+  out->scs = h->sum_scs / (double)h->n_scs;
   return ME_OK;
 }
 

@@ -196,6 +196,13 @@ ME_API int  me_get_entropies(me_ctx *ctx, int which, double *entropies_host);
  * release with me_free.  Not sharded: every rank computes the whole (cheap) voxel stage. */
 ME_API int  me_eval_awd(me_ctx *ctx, double voxel_size, int32_t min_points, int32_t scs_radius, me_awd_result *out,
                  int64_t *n_rows, double **rows27);
+/* The voxel-pair half of calculateVMD on GIVEN voxel Gaussians: rows27 = n_rows x 27 in the column layout of
+ * voxel_errors.txt (map_eval.cpp:292-302: vmin[3] vmax[3] mu_est[3] W n_gt n_est sigma_est[6] mu_gt[3] sigma_gt[6]).
+ * Recomputes W per row (w_out, nullable) with the device implementation of computeWassersteinDistanceGaussian
+ * (voxel_calculator.cpp:115-140) and AWD / SCS over those voxels (map_eval.cpp:324-325, 351-387).  This is how the
+ * tests pin the kernels to the sample output the reference ships (map_eval/scripts/voxel_errors.txt). */
+ME_API int  me_awd_from_rows(me_ctx *ctx, const double *rows27, int64_t n_rows, double voxel_size, int32_t scs_radius,
+                      double *w_out, me_awd_result *out);
 ME_API void me_free(void *p);
 
 /* timing of the last call of each stage in milliseconds (CUDA events on the context's stream):
