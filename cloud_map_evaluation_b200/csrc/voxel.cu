@@ -25,39 +25,48 @@ static constexpr int kThreads = 256;
 
 // ---- per-voxel moments -----------------------------------------------------------------------------------------
 // out: cnt[nvoxels] (int32), mom[nvoxels * 9] = S1(3), S2(xx,xy,xz,yy,yz,zz) about the voxel centre
+// One HALF-warp per voxel (a voxel is m x m x-runs; with m = 4 that is 16 runs — one per lane of the half-warp).
 __global__ void __launch_bounds__(kThreads)
 voxel_moments_kernel(const P4 *__restrict__ S, const uint32_t *__restrict__ cell_off, Lattice L,
                      int32_t *__restrict__ cnt, double *__restrict__ mom, unsigned long long *__restrict__ n_occupied) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int sub = threadIdx.x & 15;
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 4;
+  const long long ngroups = ((long long)gridDim.x * blockDim.x) >> 4;
   const int m = L.m;
   unsigned long long occ = 0;
-  for (long long vox = warp; vox < L.nvoxels; vox += nwarps) {
-    const int vx = (int)(vox % L.nvox[0]);
-    const int vy = (int)((vox / L.nvox[0]) % L.nvox[1]);
-    const int vz = (int)(vox / ((long long)L.nvox[0] * L.nvox[1]));
-    const double cx = ((double)(L.k_lo[0] + vx) + 0.5) * L.v, cy = ((double)(L.k_lo[1] + vy) + 0.5) * L.v,
-                 cz = ((double)(L.k_lo[2] + vz) + 0.5) * L.v;
+  // both half-warps of a warp iterate the same number of times (the shuffles below are full-warp)
+  const long long iters = (L.nvoxels + ngroups - 1) / ngroups;
+  for (long long it = 0; it < iters; ++it) {
+    const long long vox = group + it * ngroups;
+    const bool live = vox < L.nvoxels;
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int n = 0;
-    for (int t = lane; t < m * m; t += 32) {
-      const long long z = (long long)vz * m + t / m, y = (long long)vy * m + t % m;
-      const long long row = (z * L.dims[1] + y) * (long long)L.dims[0] + (long long)vx * m;
-      const uint32_t b = __ldg(cell_off + row), e = __ldg(cell_off + row + m);
-      for (uint32_t j = b; j < e; ++j) {
-        const P4 p = load_p4(S + j);
-        const double dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
-        n++;
-        s[0] += dx; s[1] += dy; s[2] += dz;
-        s[3] += dx * dx; s[4] += dx * dy; s[5] += dx * dz; s[6] += dy * dy; s[7] += dy * dz; s[8] += dz * dz;
+    if (live) {
+      const int vx = (int)(vox % L.nvox[0]);
+      const int vy = (int)((vox / L.nvox[0]) % L.nvox[1]);
+      const int vz = (int)(vox / ((long long)L.nvox[0] * L.nvox[1]));
+      const double cx = ((double)(L.k_lo[0] + vx) + 0.5) * L.v, cy = ((double)(L.k_lo[1] + vy) + 0.5) * L.v,
+                   cz = ((double)(L.k_lo[2] + vz) + 0.5) * L.v;
+      for (int t = sub; t < m * m; t += 16) {
+        const long long z = (long long)vz * m + t / m, y = (long long)vy * m + t % m;
+        const long long row = (z * L.dims[1] + y) * (long long)L.dims[0] + (long long)vx * m;
+        const uint32_t b = __ldg(cell_off + row), e = __ldg(cell_off + row + m);
+        for (uint32_t j = b; j < e; ++j) {
+          const P4 p = load_p4(S + j);
+          const double dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+          n++;
+          s[0] += dx; s[1] += dy; s[2] += dz;
+          s[3] += dx * dx; s[4] += dx * dy; s[5] += dx * dz; s[6] += dy * dy; s[7] += dy * dz; s[8] += dz * dz;
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    for (int o = 8; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s[k] = warp_sum(s[k]);
-    if (lane == 0) {
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (live && sub == 0) {
       cnt[vox] = n;
       if (n > 0) {
         occ++;
@@ -66,7 +75,7 @@ voxel_moments_kernel(const P4 *__restrict__ S, const uint32_t *__restrict__ cell
       }
     }
   }
-  if (lane == 0 && occ) atomicAdd(n_occupied, occ);
+  if (sub == 0 && occ) atomicAdd(n_occupied, occ);
 }
 
 // ---- 3x3 algebra (fp64) ---------------------------------------------------------------------------------------
@@ -385,10 +394,10 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
   ME_LAUNCH_CHECK(ctx);
   {
     StageTimer timer(ctx, 6);
-    int blocks_e = (int)std::min<long long>((Le.nvoxels * 32 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
+    int blocks_e = (int)std::min<long long>((Le.nvoxels * 16 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
     voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, E.d_cell_off, Le, cnt_e, mom_e, occ);
     ME_LAUNCH_CHECK(ctx);
-    int blocks_g = (int)std::min<long long>((Lg.nvoxels * 32 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
+    int blocks_g = (int)std::min<long long>((Lg.nvoxels * 16 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
     voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, G.d_cell_off, Lg, cnt_g, mom_g, occ + 1);
     ME_LAUNCH_CHECK(ctx);
   }
