@@ -74,6 +74,11 @@ class me_awd_result(C.Structure):
                 ("n_old", C.c_int64), ("n_new", C.c_int64)]
 
 
+class me_icp_result(C.Structure):
+    _fields_ = [("transformation", C.c_double * 16), ("fitness", C.c_double), ("inlier_rmse", C.c_double),
+                ("n_corr", C.c_int64), ("iterations", C.c_int32), ("converged", C.c_int32)]
+
+
 def make_nn_params(tau, icp_max_distance=1.0, cutoff_mode=ME_CUTOFF_SQDIST_LE_R, pairing=ME_PAIRING_AS_WRITTEN,
                    want_full_cd=True, directions=0):
     p = me_nn_params()

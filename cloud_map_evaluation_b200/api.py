@@ -99,6 +99,18 @@ class MapEvalB200:
         T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
         self._check(self._L.me_transform(self._ctx, which, T.ctypes.data_as(C.POINTER(C.c_double))))
 
+    def performICPRegistration(self, max_correspondence_distance, T_init=None, max_iteration=30, relative_fitness=1e-6,
+                               relative_rmse=1e-6):
+        """map_eval.cpp:1366-1394 case 0: RegistrationICP + TransformationEstimationPointToPoint; the estimated cloud held
+        by the context is transformed by the result.  Returns (T 4x4, me_icp_result)."""
+        T = np.ascontiguousarray(np.eye(4) if T_init is None else T_init, dtype=np.float64).reshape(16)
+        out = A.me_icp_result()
+        self._check(self._L.me_icp_point_to_point(self._ctx, float(max_correspondence_distance), int(max_iteration),
+                                                  float(relative_fitness), float(relative_rmse),
+                                                  T.ctypes.data_as(C.POINTER(C.c_double)), C.byref(out)))
+        self._keep[A.ME_CLOUD_EST] = None
+        return np.array(list(out.transformation)).reshape(4, 4), out
+
     def voxel_downsample(self, which, voxel_size):
         """PointCloud::VoxelDownSample on the held cloud (map_eval.cpp:38-39); returns the new point count."""
         n = C.c_int64(0)

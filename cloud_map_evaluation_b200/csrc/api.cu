@@ -242,6 +242,13 @@ int me_get_cloud(me_ctx *ctx, int which, double *xyz_host, int64_t capacity_poin
   return ME_OK;
 }
 
+int me_icp_point_to_point(me_ctx *ctx, double max_correspondence_distance, int32_t max_iteration, double relative_fitness,
+                          double relative_rmse, const double T_init[16], me_icp_result *out) {
+  ME_ENTER(ctx);
+  if (!T_init || !out) return fail(ctx, ME_ERR_INVALID, "null argument");
+  return run_icp(ctx, max_correspondence_distance, max_iteration, relative_fitness, relative_rmse, T_init, out);
+}
+
 int me_build_grid(me_ctx *ctx, int which) {
   ME_ENTER(ctx);
   if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad cloud id");

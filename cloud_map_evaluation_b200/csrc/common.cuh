@@ -170,6 +170,8 @@ int unsort_entropy(me_ctx *ctx, int which, double *h_entropy);
 int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
             double **rows27);
 int transform_cloud(me_ctx *ctx, int which, const double T[16]);
+int run_icp(me_ctx *ctx, double max_dist, int max_iter, double rel_fitness, double rel_rmse, const double T_init[16],
+            me_icp_result *out);
 int run_awd_rows(me_ctx *ctx, const double *rows27, int64_t n_rows, double voxel_size, int scs_radius, double *w_out,
                  me_awd_result *out);
 

@@ -128,6 +128,27 @@ inline void dumpParam(const Param &p, std::ostream &os) {
 }
 
 // Eigen's default IOFormat for `vec.transpose()`: coefficients right-aligned to a common width, one space apart
+// Eigen's operator<< for a 4x4 matrix: rows on separate lines, every coefficient right-aligned to the widest one
+inline std::string eigenMatrix4(const double *T, int precision) {
+  std::string cell[16];
+  size_t w = 0;
+  for (int i = 0; i < 16; ++i) {
+    std::ostringstream os;
+    os << std::fixed << std::setprecision(precision) << T[i];
+    cell[i] = os.str();
+    w = std::max(w, cell[i].size());
+  }
+  std::string out;
+  for (int r = 0; r < 4; ++r) {
+    if (r) out += "\n";
+    for (int c = 0; c < 4; ++c) {
+      if (c) out += " ";
+      out += std::string(w - cell[r * 4 + c].size(), ' ') + cell[r * 4 + c];
+    }
+  }
+  return out;
+}
+
 inline std::string eigenRow(const double *v, int n, int precision) {
   std::vector<std::string> s(n);
   size_t w = 0;
@@ -189,6 +210,7 @@ class MapEvalB200 {
   int process();                                   // map_eval.cpp:4-102
   int computeMME();                                // map_eval.cpp:149-189
   int calculateMetricsWithInitialMatrix();         // map_eval.cpp:1204-1260
+  int performRegistration();                       // map_eval.cpp:191-237, 1366-1394 (point-to-point ICP only), 1147-1202
   int calculateVMD();                              // map_eval.cpp:240-390
   void saveMmeResults();                           // map_eval.cpp:392-421 (text line only)
   void saveRegistrationResults();                  // map_eval.cpp:424-482 (text lines only)
@@ -279,11 +301,8 @@ inline int MapEvalB200::process() {
     if (param_.enable_debug) std::cout << "INFO: Using initial matrix without registration." << std::endl;
     if (calculateMetricsWithInitialMatrix() != 0) return -1;
   } else {
-    // map_eval.cpp:81 -> performRegistration(): Open3D ICP / GICP, a third-party solver outside the hot path
-    std::cerr << "ERROR: evaluate_using_initial: false needs ICP registration, which is not part of the B200 hot path "
-                 "(SURVEY.md §8f N2). Align the clouds first (initial_matrix) and set evaluate_using_initial: true."
-              << std::endl;
-    return -1;
+    // map_eval.cpp:81 -> performRegistration() -> performICPRegistration() (:1366-1394) -> calculateMetrics(reg) (:1147-1202)
+    if (performRegistration() != 0) return -1;
   }
   if (calculateVMD() != 0) return -1;
   if (param_.enable_debug) std::cout << "INFO: VMD calculation completed." << std::endl;
@@ -351,6 +370,56 @@ inline int MapEvalB200::calculateMetricsWithInitialMatrix() {
   std::cout << "INFO: est-gt MME: " << mme_est << " " << mme_gt << std::endl;
   std::cout << "INFO: IoU: " << eigenRow(nn_.iou, 5, 6) << std::endl;
   std::cout << "INFO: Full Chamfer distance (not computed by the reference on this path): " << nn_.full_cd << std::endl;
+  return 0;
+}
+
+inline int MapEvalB200::performRegistration() {
+  TicToc tic_toc;
+  if (param_.evaluation_method_ != 0) {
+    std::cerr << "ERROR: registration_methods: " << param_.evaluation_method_ << " ("
+              << (param_.evaluation_method_ == 1 ? "point-to-plane ICP" : param_.evaluation_method_ == 2 ? "generalized ICP" : "invalid")
+              << ") is not part of the B200 path (SURVEY.md §8f N2): use registration_methods: 0 (point-to-point ICP), or align "
+                 "the clouds first (initial_matrix) and set evaluate_using_initial: true." << std::endl;
+    return -1;
+  }
+  if (gpus_.size() > 1) std::cout << "INFO: ICP runs on GPU " << param_.gpu_device_ << " only; the metric sweeps are sharded." << std::endl;
+  // ICP needs all correspondences on one GPU: run it on a single-shard context, then hand every GPU the aligned cloud
+  me_icp_result reg{};
+  me_set_shard(ctx_, 0, 1);
+  const int rc = me_icp_point_to_point(ctx_, param_.icp_max_distance_, 30, 1e-6, 1e-6, param_.initial_matrix_, &reg);
+  me_set_shard(ctx_, 0, gpus_.size());
+  if (rc != ME_OK) return fail("me_icp_point_to_point");
+  t4 = tic_toc.toc();
+  std::cout << "INFO: ICP registration time: " << (t4 - t3) / 1000.0 << " [s]" << std::endl;
+  std::cout << "INFO: Aligned transformation: \n" << eigenMatrix4(reg.transformation, 6) << std::endl;
+  std::cout << "INFO: ICP overlap ratio: " << reg.fitness << std::endl;
+  std::cout << "INFO: ICP correspondences RMSE: " << reg.inlier_rmse << std::endl;
+  std::cout << "INFO: ICP correspondences size: " << reg.n_corr << std::endl;
+  file_result << std::fixed << std::setprecision(5) << "Aligned cloud: " << eigenMatrix4(reg.transformation, 5) << std::endl;
+  file_result << std::fixed << std::setprecision(5) << "Aligned results: " << reg.fitness << " " << reg.n_corr << std::endl;
+  // the other GPUs apply the same transformation to their copy of the (down-sampled) cloud
+  for (int r = 1; r < gpus_.size(); ++r)
+    if (me_transform(gpus_.ctx(r), ME_CLOUD_EST, reg.transformation) != ME_OK) return fail("me_transform (aligned cloud)");
+  // calculateMetrics(reg) (:1147-1202): est->gt on the ICP correspondences (NN within R, strict), gt->est through
+  // EvaluateRegistration(gt, est, R) (:1168), cd_vec (:1171), full Chamfer distance (:1194)
+  TicToc tic;
+  me_nn_params p{};
+  for (int i = 0; i < 5; ++i) p.tau[i] = param_.trunc_dist_[i];
+  p.icp_max_distance = param_.icp_max_distance_;
+  p.cutoff_mode = ME_CUTOFF_DIST_LT_R;
+  p.pairing = ME_PAIRING_GEOMETRIC;
+  p.want_full_cd = 1;
+  p.directions = 3;
+  std::vector<me_nn_accum> e2g(gpus_.size()), g2e(gpus_.size());
+  if (gpus_.for_each([&](int r, me_ctx *c) { return me_eval_nn_accum(c, &p, &e2g[r], &g2e[r]); }) != ME_OK) return fail("me_eval_nn_accum");
+  if (!gpus_.reduce_nn(e2g, g2e)) return fail("all-reduce of the NN accumulators");
+  if (me_nn_finalize(&p, &e2g[0], &g2e[0], n_est_, n_gt_, &nn_) != ME_OK) return fail("me_nn_finalize");
+  t_acc = tic.toc() / 1000.0;
+  full_chamfer_dist = nn_.full_cd;
+  t_fcd = t_acc;
+  t5 = tic_toc.toc();
+  std::cout << "INFO: Chamfer Distance: " << eigenRow(nn_.cd, 5, 6) << std::endl;
+  std::cout << "INFO: Full Chamfer Distance: " << full_chamfer_dist << std::endl;
   return 0;
 }
 

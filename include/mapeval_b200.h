@@ -142,6 +142,15 @@ typedef struct {
   int64_t n_active, n_old, n_new;    /* voxel_calculator.cpp:170 */
 } me_awd_result;
 
+/* ---- N2: point-to-point ICP (registration_methods: 0) -------------------------------------------------- */
+
+typedef struct {             /* == open3d RegistrationResult (map_eval.cpp:1367-1394) */
+  double  transformation[16];        /* row-major 4x4: registration_result.transformation_ -> trans            */
+  double  fitness, inlier_rmse;      /* fitness_ (|corr| / |est|), inlier_rmse_                                  */
+  int64_t n_corr;                    /* correspondence_set_.size()                                               */
+  int32_t iterations, converged;     /* updates applied; 1 if the relative criteria stopped the loop             */
+} me_icp_result;
+
 /* ---- lifecycle ---------------------------------------------------------------------------------- */
 
 ME_API int  me_abi_version(void);
@@ -168,6 +177,14 @@ ME_API int  me_voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64
 /* the cloud currently held by the context (after me_transform / me_voxel_downsample), caller order, N x 3 fp64.
  * xyz_host == NULL: size query only (*n).  capacity_points < N is an error. */
 ME_API int  me_get_cloud(me_ctx *ctx, int which, double *xyz_host, int64_t capacity_points, int64_t *n);
+/* replaces: MapEval::performICPRegistration case 0 (map_eval.cpp:1366-1394): open3d RegistrationICP(est, gt,
+ * icp_max_distance, initial_matrix, TransformationEstimationPointToPoint(), ICPConvergenceCriteria{relative_fitness,
+ * relative_rmse, max_iteration} = {1e-6, 1e-6, 30}).  On return the estimated cloud held by the context is the original
+ * cloud transformed once by the result (map_3d_->Transform(trans), :1392), ready for me_eval_nn with
+ * ME_CUTOFF_DIST_LT_R / ME_PAIRING_GEOMETRIC / want_full_cd (calculateMetrics, :1147-1202).  world must be 1.
+ * Point-to-plane (case 1) and generalized ICP (case 2) are not provided. */
+ME_API int  me_icp_point_to_point(me_ctx *ctx, double max_correspondence_distance, int32_t max_iteration,
+                           double relative_fitness, double relative_rmse, const double T_init[16], me_icp_result *out);
 /* builds (or rebuilds) the cell-sorted grid of one cloud; the eval calls build lazily if needed */
 ME_API int  me_build_grid(me_ctx *ctx, int which);
 

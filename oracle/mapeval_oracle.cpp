@@ -726,4 +726,121 @@ int oracle_voxel_downsample(const double *xyz, int64_t n, double voxel_size, int
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// [ext-icp] open3d::pipelines::registration::RegistrationICP with TransformationEstimationPointToPoint and the default
+// ICPConvergenceCriteria (relative_fitness 1e-6, relative_rmse 1e-6, max_iteration 30), as called by
+// MapEval::performICPRegistration case 0 (map_eval.cpp:1370-1374).  Open3D 0.15-0.17 Registration.cpp (not vendored):
+//   pcd = source transformed by init;  result = GetRegistrationResultAndCorrespondences(pcd, target, kdtree, R, T)
+//   loop: update = umeyama(corr, no scaling); T = update * T; pcd.Transform(update); backup = result; result = ...;
+//         stop when |d fitness| < 1e-6 and |d rmse| < 1e-6
+//   correspondences: KDTreeFlann::SearchHybrid(p, R, 1): nearest neighbour kept iff d2 < R*R (lower_bound: strict);
+//   error2 += d2; fitness = |corr| / |source|; inlier_rmse = sqrt(error2 / |corr|).
+// Eigen::umeyama (3.3.x): sigma = (1/n) dst_demean src_demean^T, JacobiSVD, S(2) = -1 if det(U) det(V) < 0,
+// R = U S V^T, t = dst_mean - R src_mean.  The SVD is restated as a one-sided Jacobi (Hestenes) iteration.
+// ---------------------------------------------------------------------------------------------------
+static void svd3_one_sided_jacobi(const double a_in[9], double U[9], double w[3], double V[9]) {
+  double a[9];
+  for (int i = 0; i < 9; ++i) { a[i] = a_in[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < 3; ++k) { alpha += a[k * 3 + p] * a[k * 3 + p]; beta += a[k * 3 + q] * a[k * 3 + q]; gamma += a[k * 3 + p] * a[k * 3 + q]; }
+        off = std::max(off, std::fabs(gamma) / std::sqrt(std::max(alpha * beta, 1e-300)));
+        if (gamma == 0.0) continue;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+        for (int k = 0; k < 3; ++k) {
+          const double ap = a[k * 3 + p], aq = a[k * 3 + q];
+          a[k * 3 + p] = c * ap - sn * aq; a[k * 3 + q] = sn * ap + c * aq;
+          const double vp = V[k * 3 + p], vq = V[k * 3 + q];
+          V[k * 3 + p] = c * vp - sn * vq; V[k * 3 + q] = sn * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  for (int j = 0; j < 3; ++j) {
+    double nrm = 0;
+    for (int k = 0; k < 3; ++k) nrm += a[k * 3 + j] * a[k * 3 + j];
+    w[j] = std::sqrt(nrm);
+  }
+  // sort singular values descending (JacobiSVD convention), columns of U = a_j / w_j
+  int ord[3] = {0, 1, 2};
+  std::sort(ord, ord + 3, [&](int x, int y) { return w[x] > w[y]; });
+  double a2[9], V2[9], w2[3];
+  for (int j = 0; j < 3; ++j) { w2[j] = w[ord[j]]; for (int k = 0; k < 3; ++k) { a2[k * 3 + j] = a[k * 3 + ord[j]]; V2[k * 3 + j] = V[k * 3 + ord[j]]; } }
+  for (int j = 0; j < 3; ++j) { w[j] = w2[j]; for (int k = 0; k < 3; ++k) { V[k * 3 + j] = V2[k * 3 + j]; U[k * 3 + j] = w2[j] > 0 ? a2[k * 3 + j] / w2[j] : 0.0; } }
+  if (w[2] <= 1e-300 * w[0] || w[2] == 0.0) {      // rank deficient: complete U with the cross product of its first two columns
+    U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
+  }
+}
+static double det3h(const double *m) {
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+struct IcpEval { double fitness, rmse; int64_t n_corr; std::vector<int32_t> idx; std::vector<char> keep; };
+static void icp_evaluate(const KdTree &tree, const double *pcd, int64_t n, double R, IcpEval &ev) {
+  ev.idx.resize(n); ev.keep.resize(n);
+  double err2 = 0; int64_t nc = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : err2, nc)
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t bi; double bd;
+    tree.knn1(pcd + 3 * i, bi, bd);
+    ev.idx[i] = bi;
+    ev.keep[i] = (bi >= 0 && bd < R * R) ? 1 : 0;
+    if (ev.keep[i]) { err2 += bd; nc++; }
+  }
+  ev.n_corr = nc;
+  ev.fitness = n > 0 ? (double)nc / (double)n : 0.0;
+  ev.rmse = nc > 0 ? std::sqrt(err2 / (double)nc) : 0.0;
+}
+
+int oracle_icp_point_to_point(const double *est, int64_t n_est, const double *gt, int64_t n_gt, double max_dist,
+                              int max_iter, double rel_fitness, double rel_rmse, const double T_init[16], double T_out[16],
+                              double *fitness, double *inlier_rmse, int64_t *n_corr, int32_t *iterations) {
+  KdTree tree;
+  tree.build(gt, n_gt);
+  std::vector<double> pcd(est, est + 3 * n_est);
+  double T[16];
+  std::memcpy(T, T_init, sizeof(T));
+  oracle_transform(pcd.data(), n_est, T);
+  IcpEval res, backup;
+  icp_evaluate(tree, pcd.data(), n_est, max_dist, res);
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    if (res.n_corr == 0) break;      // Open3D would feed umeyama an empty set; nothing can be estimated
+    double ms[3] = {0, 0, 0}, md[3] = {0, 0, 0};
+    for (int64_t i = 0; i < n_est; ++i)
+      if (res.keep[i]) for (int a = 0; a < 3; ++a) { ms[a] += pcd[3 * i + a]; md[a] += gt[3ll * res.idx[i] + a]; }
+    const double n = (double)res.n_corr;
+    for (int a = 0; a < 3; ++a) { ms[a] /= n; md[a] /= n; }
+    double sigma[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < n_est; ++i)
+      if (res.keep[i])
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) sigma[r * 3 + c] += (gt[3ll * res.idx[i] + r] - md[r]) * (pcd[3 * i + c] - ms[c]);
+    for (int k = 0; k < 9; ++k) sigma[k] /= n;
+    double U[9], w[3], V[9], S[3] = {1, 1, 1};
+    svd3_one_sided_jacobi(sigma, U, w, V);
+    if (det3h(U) * det3h(V) < 0) S[2] = -1;
+    double upd[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += U[r * 3 + k] * S[k] * V[c * 3 + k]; upd[r * 4 + c] = v; }
+    for (int r = 0; r < 3; ++r) upd[r * 4 + 3] = md[r] - (upd[r * 4] * ms[0] + upd[r * 4 + 1] * ms[1] + upd[r * 4 + 2] * ms[2]);
+    double Tn[16];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) { double v = 0; for (int k = 0; k < 4; ++k) v += upd[r * 4 + k] * T[k * 4 + c]; Tn[r * 4 + c] = v; }
+    std::memcpy(T, Tn, sizeof(T));
+    oracle_transform(pcd.data(), n_est, upd);
+    backup = res;
+    icp_evaluate(tree, pcd.data(), n_est, max_dist, res);
+    if (std::fabs(backup.fitness - res.fitness) < rel_fitness && std::fabs(backup.rmse - res.rmse) < rel_rmse) { ++it; break; }
+  }
+  std::memcpy(T_out, T, sizeof(T));
+  *fitness = res.fitness; *inlier_rmse = res.rmse; *n_corr = res.n_corr; *iterations = it;
+  return 0;
+}
+
 }  // extern "C"

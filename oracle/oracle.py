@@ -44,6 +44,8 @@ def lib():
         L.oracle_scs.argtypes = [ip, dp, C.c_int64, C.c_int, dp, C.POINTER(C.c_int64)]
         L.oracle_voxel_map.argtypes = [dp, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.POINTER(ip),
                                        C.POINTER(ip), C.POINTER(dp), C.POINTER(dp)]
+        L.oracle_icp_point_to_point.argtypes = [dp, C.c_int64, dp, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double, dp, dp,
+                                                dp, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.oracle_voxel_downsample.argtypes = [dp, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.POINTER(dp)]
         _lib = L
     return _lib
@@ -165,3 +167,16 @@ def voxel_downsample(xyz, voxel_size):
     res = np.ctypeslib.as_array(out, shape=(n_out.value, 3)).copy()
     lib().oracle_free(out)
     return res
+
+
+def icp_point_to_point(est, gt, max_dist, T_init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """open3d RegistrationICP + TransformationEstimationPointToPoint (map_eval.cpp:1370-1374).
+    Returns (T 4x4, fitness, inlier_rmse, n_corr, iterations)."""
+    e, g = _cloud(est), _cloud(gt)
+    Ti = np.ascontiguousarray(np.eye(4) if T_init is None else T_init, dtype=np.float64).reshape(16)
+    To = np.empty(16, np.float64)
+    fit, rm = C.c_double(0), C.c_double(0)
+    nc, it = C.c_int64(0), C.c_int32(0)
+    lib().oracle_icp_point_to_point(_dptr(e), e.shape[0], _dptr(g), g.shape[0], float(max_dist), int(max_iter), float(rel_fitness),
+                                    float(rel_rmse), _dptr(Ti), _dptr(To), C.byref(fit), C.byref(rm), C.byref(nc), C.byref(it))
+    return To.reshape(4, 4), fit.value, rm.value, nc.value, it.value

@@ -456,3 +456,33 @@ def test_tiny_and_degenerate_clouds(api, O):
             ctx.calculateMetricsWithInitialMatrix(p)
         with pytest.raises(api.MapEvalError):
             ctx.computeMME(A.ME_CLOUD_EST, 0.1, 10)
+
+
+@pytest.mark.parametrize("max_dist", [0.15, 1.0])
+def test_icp_point_to_point_and_path_b(api, O, max_dist):
+    """registration_methods: 0 — RegistrationICP + TransformationEstimationPointToPoint (map_eval.cpp:1366-1394), then the
+    path-B metrics of calculateMetrics(reg) (:1147-1202) on the aligned cloud."""
+    est, gt, cfg = synth.make_pair("C1", scale=0.3)
+    th = np.deg2rad(1.5)
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    c = gt.mean(0)
+    src = np.ascontiguousarray((est - c) @ Rz.T + c + np.array([0.02, -0.015, 0.01]))
+    T0 = np.eye(4)
+    T0[:3, 3] = [0.001, 0.0, -0.002]
+    with _ctx(api, src, gt) as ctx:
+        T, reg = ctx.performICPRegistration(max_dist, T0)
+        aligned = ctx.get_cloud(A.ME_CLOUD_EST)
+        p = A.make_nn_params(cfg["tau"], max_dist, cutoff_mode=A.ME_CUTOFF_DIST_LT_R, pairing=A.ME_PAIRING_GEOMETRIC)
+        nn = ctx.calculateMetricsWithInitialMatrix(p)          # = calculateMetrics(reg) on the aligned cloud
+    To, fit, rmse, nc, it = O.icp_point_to_point(src, gt, max_dist, T0)
+    assert (reg.n_corr, reg.iterations) == (nc, it)
+    np.testing.assert_allclose(T, To, atol=1e-10)
+    np.testing.assert_allclose([reg.fitness, reg.inlier_rmse], [fit, rmse], rtol=1e-9)
+    oaligned = O.transform(src, To)
+    np.testing.assert_allclose(aligned, oaligned, atol=1e-9)
+    # the registration improves on the initial guess
+    T1, reg1 = None, None
+    with _ctx(api, src, gt) as ctx:
+        _, reg0 = ctx.performICPRegistration(max_dist, T0, max_iteration=0)
+    assert reg.inlier_rmse <= reg0.inlier_rmse and reg0.iterations == 0
+    _cmp_nn(nn, O.eval_nn(aligned, gt, p))

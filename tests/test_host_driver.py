@@ -186,10 +186,28 @@ def test_map_eval_end_to_end(exe, tmp_path):
     np.testing.assert_allclose(cdf[:, 0], np.sort(orows[:, 9]), rtol=1e-5)
     np.testing.assert_allclose(cdf[:, 1], (np.arange(len(cdf)) + 1) / len(cdf), rtol=1e-5)
     assert "INFO: Spatial Consistency Score (SCS):" in out.stdout and "MME EST-GT:" in out.stdout
-    # evaluate_using_initial: false needs ICP, which is outside the hot path: process() returns -1
+    # evaluate_using_initial: false with generalized ICP (registration_methods: 2, the shipped default) is not provided
     cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false"))
     out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
-    assert out.returncode != 0 and "ICP" in out.stderr
+    assert out.returncode != 0 and "generalized ICP" in out.stderr
+    # ... point-to-point ICP (registration_methods: 0) is: path B = ICP + calculateMetrics(reg)
+    cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false")
+                    .replace("registration_methods: 2", "registration_methods: 0"))
+    (est_dir / "map_results" / "map_results.txt").unlink()
+    out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = (est_dir / "map_results" / "map_results.txt").read_text().splitlines()
+    i0 = next(i for i, l in enumerate(res) if l.startswith("Aligned cloud:"))
+    Tm = np.array([[float(x) for x in res[i0].split(":", 1)[1].split()]] + [[float(x) for x in res[i0 + k].split()] for k in (1, 2, 3)])
+    To, fit, rmse, nc, it = O.icp_point_to_point(est, gt, 1.0)
+    np.testing.assert_allclose(Tm, To, atol=6e-6)                 # printed with setprecision(5)
+    line = {l.split(":")[0]: l.split(":", 1)[1].split() for l in res if ":" in l}
+    assert int(line["Aligned results"][1]) == nc and abs(float(line["Aligned results"][0]) - fit) < 6e-6
+    aligned = O.transform(est, To)
+    pb = A.make_nn_params([0.2, 0.1, 0.08, 0.05, 0.01], 1.0, cutoff_mode=A.ME_CUTOFF_DIST_LT_R, pairing=A.ME_PAIRING_GEOMETRIC)
+    onb = O.eval_nn(aligned, gt, pb)
+    np.testing.assert_allclose([float(x) for x in line["RMSE/AC"]], list(onb.est_to_gt.rmse), rtol=1e-7, atol=1e-12)
+    assert abs(float(line["FULL CD"][0]) - onb.full_cd) < 6e-6     # path B computes the full Chamfer distance (:1194)
 
 
 @pytest.mark.gpu

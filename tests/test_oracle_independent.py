@@ -190,3 +190,42 @@ def test_voxel_downsample_against_numpy():
         m = sums / np.bincount(inv.ravel())[:, None]
         assert o.shape == m.shape
         np.testing.assert_array_equal(o, m)      # np.unique sorts rows lexicographically = increasing (ix, iy, iz)
+
+
+def test_icp_point_to_point_against_numpy_scipy():
+    """oracle_icp_point_to_point (restating Open3D RegistrationICP + Eigen::umeyama) vs an independent numpy / cKDTree
+    statement of the same loop."""
+    from scipy.spatial import cKDTree
+    from cloud_map_evaluation_b200 import synth
+    est, gt, cfg = synth.make_pair("C1", scale=0.1)
+    th = np.deg2rad(2.0)
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    c = gt.mean(0)
+    src = (est - c) @ Rz.T + c + np.array([0.03, -0.02, 0.01])
+    R = 0.2
+    tree = cKDTree(gt)
+
+    def step(pcd):
+        d, i = tree.query(pcd, k=1)
+        keep = d * d < R * R
+        p, q = pcd[keep], gt[i[keep]]
+        ms, md = p.mean(0), q.mean(0)
+        U, s, Vt = np.linalg.svd(((q - md).T @ (p - ms)) / len(p))
+        S = np.eye(3)
+        if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+            S[2, 2] = -1
+        T = np.eye(4)
+        T[:3, :3] = U @ S @ Vt
+        T[:3, 3] = md - T[:3, :3] @ ms
+        return T, int(keep.sum()), float(np.sqrt((d[keep] ** 2).sum() / keep.sum()))
+
+    T, pcd = np.eye(4), src.copy()
+    for _ in range(4):
+        upd, _, _ = step(pcd)
+        T = upd @ T
+        pcd = pcd @ upd[:3, :3].T + upd[:3, 3]
+    _, nc, rm = step(pcd)
+    To, fit, rmo, nco, ito = O.icp_point_to_point(src, gt, R, max_iter=4, rel_fitness=0.0, rel_rmse=0.0)
+    assert ito == 4 and nco == nc
+    np.testing.assert_allclose(To, T, atol=1e-13)
+    np.testing.assert_allclose([fit, rmo], [nc / len(src), rm], rtol=1e-12)
