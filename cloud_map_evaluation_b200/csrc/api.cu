@@ -108,7 +108,7 @@ int me_create(const me_options *opt, me_ctx **out) {
   ctx->rank = opt->rank; ctx->world = opt->world;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->nn_cell_size = opt->nn_cell_size > 0 ? opt->nn_cell_size : 0.0;
-  ctx->max_grid_cells = opt->max_grid_cells > 0 ? std::min<long long>(opt->max_grid_cells, 0xfffffff0ll) : (1ll << 28);
+  ctx->max_grid_cells = opt->max_grid_cells > 0 ? std::min<long long>(opt->max_grid_cells, 0xfffffff0ll) : 0;   // 0 = automatic
   ctx->voxel_hint = opt->vmd_voxel_size > 0 ? opt->vmd_voxel_size : 0.0;
   if (opt->stream) { ctx->stream = (cudaStream_t)opt->stream; ctx->own_stream = false; }
   else {

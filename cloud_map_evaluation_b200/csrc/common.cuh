@@ -89,7 +89,7 @@ struct me_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   double nn_cell_size = 0.0;
-  long long max_grid_cells = 1ll << 28;
+  long long max_grid_cells = 0;     // budget of the dense cell table; 0 = automatic (grid_budget)
   double voxel_hint = 0.0;          // lattice alignment requested by the voxel stage
   // lattice spec shared by both clouds, so that their cells coincide (same v, m; integer index offsets)
   double spec_v = 0.0;

@@ -443,6 +443,15 @@ int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
   return ME_OK;
 }
 
+// Budget of the dense cell table (4 B per cell).  Automatic: 2^28 cells, growing with the clouds up to 2^31 (16 cells per
+// point: a 200 M-point surface scan at 1 cm spacing keeps ~4 points per occupied cell instead of ~18; the table then
+// takes 8.6 GB of the 180 GB and ~5 ms per build to clear and scan, against sweeps of hundreds of ms at that size).
+static long long grid_budget(const me_ctx *ctx) {
+  if (ctx->max_grid_cells > 0) return ctx->max_grid_cells;
+  const long long n = std::max(ctx->cloud[0].n, ctx->cloud[1].n);
+  return std::min<long long>(1ll << 31, std::max<long long>(1ll << 28, 16 * n));
+}
+
 // solo_h > 0: lay the cloud out on a lattice of its own with cells of (about) that edge — used by the MME sweep when the
 // search radius spans many cells of the shared lattice (mme.cu).  A solo lattice is not voxel-aligned and not shared with
 // the other cloud; the next ordinary build_grid() replaces it.
@@ -456,7 +465,7 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
   ME_TRY(wait_upload(ctx, which));
   StageTimer timer(ctx, which == ME_CLOUD_EST ? 0 : 1);
   ME_TRY(compute_bbox(ctx, which));
-  const long long budget = ctx->max_grid_cells;
+  const long long budget = grid_budget(ctx);
   const double v_req = ctx->voxel_hint;
 
   // Both clouds share one lattice spec (v, m) so that their cells coincide.  The spec is re-planned whenever no

@@ -73,7 +73,7 @@ typedef struct {
   int32_t rank, world;     /* this context evaluates queries [rank*N/world,(rank+1)*N/world) */
   void   *stream;          /* cudaStream_t to launch on; NULL = library-owned stream       */
   double  nn_cell_size;    /* edge of the hashed-grid cells in metres; <= 0 = auto         */
-  int64_t max_grid_cells;  /* budget for the dense cell table; <= 0 = default (2^28)       */
+  int64_t max_grid_cells;  /* budget for the dense cell table; <= 0 = automatic (2^28 .. 2^31 with the cloud sizes) */
   double  vmd_voxel_size;  /* voxel edge the lattices should align to (the config's vmd_voxel_size);
                               <= 0 = unknown: me_eval_awd then re-lays the clouds out once     */
 } me_options;

@@ -486,3 +486,17 @@ def test_icp_point_to_point_and_path_b(api, O, max_dist):
         _, reg0 = ctx.performICPRegistration(max_dist, T0, max_iteration=0)
     assert reg.inlier_rmse <= reg0.inlier_rmse and reg0.iterations == 0
     _cmp_nn(nn, O.eval_nn(aligned, gt, p))
+
+
+def test_small_lattice_budget(api, O):
+    """A cell-table budget far below what the clouds would like (large sparse scenes hit this): the lattice coarsens
+    (tens of points per cell), the MME radius may span less than one cell, results are unchanged."""
+    est, gt, cfg = synth.make_pair("C2", scale=0.05)
+    p = A.make_nn_params(cfg["tau"], 1.0, pairing=A.ME_PAIRING_GEOMETRIC)
+    with _ctx(api, est, gt, max_grid_cells=2000, vmd_voxel_size=0.0) as ctx:
+        nn = ctx.calculateMetricsWithInitialMatrix(p)
+        mme, ent = ctx.computeMME(A.ME_CLOUD_EST, cfg["nn_radius"], 10, want_entropies=True)
+    _cmp_nn(nn, O.eval_nn(est, gt, p))
+    omme, oent = O.eval_mme(est, cfg["nn_radius"], 10, want_entropies=True)
+    assert mme.n_valid == omme.n_valid
+    np.testing.assert_allclose(ent, oent, rtol=RTOL_ENT, atol=0)
