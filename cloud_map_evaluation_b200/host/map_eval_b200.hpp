@@ -33,6 +33,7 @@
 #include "../../include/mapeval_b200.h"
 #include "cloud_io.hpp"
 #include "gpu_group.hpp"
+#include "render.hpp"
 #include "yaml_lite.hpp"
 
 namespace fs = std::filesystem;
@@ -229,6 +230,9 @@ class MapEvalB200 {
               << (!gpus_.error().empty() ? gpus_.error().c_str() : (ctx_ ? me_last_error(ctx_) : me_last_error(nullptr))) << std::endl;
     return -1;
   }
+  render::ColoredCloud map_3d_entropy_, gt_3d_entropy_, map_3d_render_raw_, map_3d_render_inlier_;   // map_eval.h:341-347
+  int renderEntropy(int which, int64_t n, render::ColoredCloud *out);
+  int renderDistances(bool cutoff_strict);
   GpuGroup gpus_;            // one context per GPU; rank r evaluates the r-th shard of every sweep's query range
   me_ctx *ctx_ = nullptr;    // = gpus_.ctx(0): the voxel stage and the single-GPU calls
   std::vector<double> map_3d_, gt_3d_;   // N x 3 fp64, the layout of open3d PointCloud::points_ (as loaded)
@@ -314,6 +318,67 @@ inline int MapEvalB200::process() {
   return 0;
 }
 
+// ColorPointCloudByMME (map_eval.cpp:686-736) on the entropies of the sweep that just ran (each GPU holds its shard)
+inline int MapEvalB200::renderEntropy(int which, int64_t n, render::ColoredCloud *out) {
+  std::vector<double> ent((size_t)n, 0.0), part((size_t)n), xyz((size_t)n * 3);
+  for (int r = 0; r < gpus_.size(); ++r) {
+    if (me_get_entropies(gpus_.ctx(r), which, part.data()) != ME_OK) { ctx_ = gpus_.ctx(r); const int rc = fail("me_get_entropies"); ctx_ = gpus_.ctx(0); return rc; }
+    for (int64_t i = 0; i < n; ++i) ent[i] += part[i];          // disjoint shards: the other ranks hold zeros
+  }
+  int64_t got = 0;
+  if (me_get_cloud(ctx_, which, xyz.data(), n, &got) != ME_OK || got != n) return fail("me_get_cloud");
+  *out = render::color_by_entropy(xyz, ent);
+  return 0;
+}
+
+// renderDistanceOnPointCloud (map_eval.cpp:586-606) for the raw map (every estimated point against the ground truth) and
+// the inlier map (the corresponding points against each other), both clipped at accuracy_level[0] (:485-487).
+inline int MapEvalB200::renderDistances(bool cutoff_strict) {
+  const int64_t n = n_est_;
+  std::vector<int32_t> idx((size_t)n, -1), pidx((size_t)n);
+  std::vector<double> d2((size_t)n, std::nan("")), pd2((size_t)n), est((size_t)n * 3), gt((size_t)n_gt_ * 3);
+  for (int r = 0; r < gpus_.size(); ++r) {
+    if (me_get_nn(gpus_.ctx(r), ME_CLOUD_EST, pidx.data(), pd2.data()) != ME_OK) return fail("me_get_nn");
+    for (int64_t i = 0; i < n; ++i)
+      if (pidx[i] >= 0) { idx[i] = pidx[i]; d2[i] = pd2[i]; }
+  }
+  int64_t got = 0;
+  if (me_get_cloud(ctx_, ME_CLOUD_EST, est.data(), n, &got) != ME_OK || got != n) return fail("me_get_cloud(est)");
+  if (me_get_cloud(ctx_, ME_CLOUD_GT, gt.data(), n_gt_, &got) != ME_OK || got != n_gt_) return fail("me_get_cloud(gt)");
+  const double dis = param_.trunc_dist_[0];
+  map_3d_render_raw_ = render::color_by_distance(est, d2, dis);
+  // corresponding_cloud_est / corresponding_cloud_gt: the kept est->gt pairs (:1083-1089); the reference's second call of
+  // getDiffRegResultWithCorrespondence on path A overwrites them with index-swapped points (:1241) — not reproduced
+  std::vector<double> ce, cg;
+  const double R = param_.icp_max_distance_;
+  for (int64_t i = 0; i < n; ++i) {
+    if (idx[i] < 0) continue;
+    if (!(cutoff_strict ? d2[i] < R * R : d2[i] <= R)) continue;
+    for (int a = 0; a < 3; ++a) { ce.push_back(est[3 * i + a]); cg.push_back(gt[3 * (size_t)idx[i] + a]); }
+  }
+  map_3d_render_inlier_ = render::ColoredCloud();
+  if (ce.empty()) return 0;
+  me_options opt{};
+  opt.abi_version = ME_ABI_VERSION; opt.device = param_.gpu_device_; opt.rank = 0; opt.world = 1;
+  me_ctx *tmp = nullptr;
+  if (me_create(&opt, &tmp) != ME_OK) return fail("me_create (inlier map)");
+  const int64_t nc = (int64_t)(ce.size() / 3);
+  me_nn_params p{};
+  p.icp_max_distance = R; p.cutoff_mode = ME_CUTOFF_DIST_LT_R; p.pairing = ME_PAIRING_GEOMETRIC; p.want_full_cd = 1; p.directions = 1;
+  me_nn_accum acc;
+  std::vector<int32_t> ci((size_t)nc);
+  std::vector<double> cd2((size_t)nc);
+  int rc = me_set_cloud(tmp, ME_CLOUD_EST, ce.data(), nc);
+  if (rc == ME_OK) rc = me_set_cloud(tmp, ME_CLOUD_GT, cg.data(), nc);
+  if (rc == ME_OK) rc = me_eval_nn_accum(tmp, &p, &acc, nullptr);
+  if (rc == ME_OK) rc = me_get_nn(tmp, ME_CLOUD_EST, ci.data(), cd2.data());
+  if (rc != ME_OK) std::cerr << "ERROR: inlier distance map: " << me_last_error(tmp) << std::endl;
+  me_destroy(tmp);
+  if (rc != ME_OK) return -1;
+  map_3d_render_inlier_ = render::color_by_distance(ce, cd2, dis);
+  return 0;
+}
+
 inline int MapEvalB200::computeMME() {
   if (!param_.evaluate_mme_) return 0;
   // use_tbb_mme only selects between two CPU threadings of the same arithmetic in the reference (:153-157)
@@ -325,12 +390,14 @@ inline int MapEvalB200::computeMME() {
     return me_mme_finalize(&acc[0], n_total, out) == ME_OK ? 0 : -1;
   };
   if (eval_mme(ME_CLOUD_EST, 10, n_est_, &mme_est_res_) != 0) return fail("me_eval_mme(est)");
+  if (param_.save_immediate_result_ && renderEntropy(ME_CLOUD_EST, n_est_, &map_3d_entropy_) != 0) return -1;   // :179
   mme_est = mme_est_res_.mme;
   if (mme_est_res_.n_valid * 100.0 / (double)mme_est_res_.n_total < 0.6)
     std::cerr << "valid points is too small, please check the input point cloud" << std::endl;   // :1732
   min_abs_entropy = mme_est_res_.min_abs_entropy; max_abs_entropy = mme_est_res_.max_abs_entropy;   // :179 -> :700-701
   if (param_.evaluate_gt_mme_) {
     if (eval_mme(ME_CLOUD_GT, 5, n_gt_, &mme_gt_res_) != 0) return fail("me_eval_mme(gt)");
+    if (param_.save_immediate_result_ && renderEntropy(ME_CLOUD_GT, n_gt_, &gt_3d_entropy_) != 0) return -1;      // :181
     mme_gt = mme_gt_res_.mme;
     std::cout << "GT MME Valid_points " << mme_gt_res_.n_valid * 100.0 / (double)mme_gt_res_.n_total << "% " << mme_gt_res_.n_valid
               << " " << mme_gt_res_.n_total << std::endl;
@@ -365,6 +432,7 @@ inline int MapEvalB200::calculateMetricsWithInitialMatrix() {
   if (!gpus_.reduce_nn(e2g, g2e)) return fail("all-reduce of the NN accumulators");
   if (me_nn_finalize(&p, &e2g[0], &g2e[0], n_est_, n_gt_, &nn_) != ME_OK) return fail("me_nn_finalize");
   t_acc = tic.toc() / 1000.0;
+  if (param_.save_immediate_result_ && renderDistances(false) != 0) return -1;
   std::cout << "INFO: Chamfer Distance: " << eigenRow(nn_.cd, 5, 6) << std::endl;
   std::cout << "INFO: F1 Score: " << eigenRow(nn_.f1, 5, 6) << std::endl;
   std::cout << "INFO: est-gt MME: " << mme_est << " " << mme_gt << std::endl;
@@ -415,6 +483,7 @@ inline int MapEvalB200::performRegistration() {
   if (!gpus_.reduce_nn(e2g, g2e)) return fail("all-reduce of the NN accumulators");
   if (me_nn_finalize(&p, &e2g[0], &g2e[0], n_est_, n_gt_, &nn_) != ME_OK) return fail("me_nn_finalize");
   t_acc = tic.toc() / 1000.0;
+  if (param_.save_immediate_result_ && renderDistances(true) != 0) return -1;
   full_chamfer_dist = nn_.full_cd;
   t_fcd = t_acc;
   t5 = tic_toc.toc();
@@ -476,7 +545,14 @@ inline void MapEvalB200::saveMmeResults() {   // map_eval.cpp:392-421
   file_result << std::fixed << std::setprecision(5) << "MME: " << mme_est << " " << mme_gt << " " << min_abs_entropy << " "
               << max_abs_entropy << std::endl;
   if (param_.enable_debug) std::cout << "INFO: MME results saved to " << results_file_path << std::endl;
-  // map_entropy.pcd / gt_entropy.pcd (rendered clouds) are not produced: SURVEY.md §8f N3
+  // map_eval.cpp:404-412
+  if (!render::write_pcd(results_subfolder + "map_entropy.pcd", map_3d_entropy_)) std::cerr << "ERROR: cannot write map_entropy.pcd" << std::endl;
+  else if (param_.enable_debug) std::cout << "INFO: Saved rendered entropy map to " << results_subfolder + "map_entropy.pcd" << std::endl;
+  if (param_.evaluate_gt_mme_) {
+    if (!render::write_pcd(results_subfolder + "gt_entropy.pcd", gt_3d_entropy_)) std::cerr << "ERROR: cannot write gt_entropy.pcd" << std::endl;
+    else if (param_.enable_debug)
+      std::cout << "INFO: Saved rendered entropy ground truth map to " << results_subfolder + "gt_entropy.pcd" << std::endl;
+  }
 }
 
 inline void MapEvalB200::saveRegistrationResults() {   // map_eval.cpp:424-482
@@ -499,5 +575,9 @@ inline void MapEvalB200::saveRegistrationResults() {   // map_eval.cpp:424-482
   file_result << "AWD+SCS Time: " << t_v / 1000.0 + (t_vmd - t_v) / 1000.0 + (t_scs - t_cdf) / 1000.0 << std::endl;
   file_result.close();
   if (param_.enable_debug) std::cout << "INFO: Results saved to " << results_subfolder + "map_results.txt" << std::endl;
-  // raw_rendered_dis_map.pcd / inlier_rendered_dis_map.pcd are not produced: SURVEY.md §8f N3
+  // map_eval.cpp:485-499
+  if (!render::write_pcd(results_subfolder + "raw_rendered_dis_map.pcd", map_3d_render_raw_)) std::cerr << "ERROR: cannot write raw_rendered_dis_map.pcd" << std::endl;
+  else if (param_.enable_debug) std::cout << "INFO: Saved raw distance error map to " << results_subfolder + "raw_rendered_dis_map.pcd" << std::endl;
+  if (!render::write_pcd(results_subfolder + "inlier_rendered_dis_map.pcd", map_3d_render_inlier_)) std::cerr << "ERROR: cannot write inlier_rendered_dis_map.pcd" << std::endl;
+  else if (param_.enable_debug) std::cout << "INFO: Saved inlier distance error map to " << results_subfolder + "inlier_rendered_dis_map.pcd" << std::endl;
 }

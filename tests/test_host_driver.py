@@ -36,6 +36,38 @@ enable_debug: false
 """
 
 
+def _jet_u8(v):
+    """open3d ColorMapJet + ColorToUint8 on an array of values."""
+    def interp(x, y0, x0, y1, x1):
+        return np.where(x < x0, y0, np.where(x > x1, y1, (x - x0) * (y1 - y0) / (x1 - x0) + y0))
+
+    def base(x):
+        return np.where(x <= -0.75, 0.0, np.where(x <= -0.25, interp(x, 0.0, -0.75, 1.0, -0.25),
+                        np.where(x <= 0.25, 1.0, np.where(x <= 0.75, interp(x, 1.0, 0.25, 0.0, 0.75), 0.0))))
+    rgb = np.stack([base(v * 2 - 1.5), base(v * 2 - 1.0), base(v * 2 - 0.5)], axis=1)
+    return np.round(np.clip(rgb, 0, 1) * 255).astype(np.uint8)
+
+
+def _entropy_colors(ent):
+    nz = ent[ent != 0]
+    max_abs, min_abs = abs(nz.min()), abs(nz.max())
+    norm = (np.abs(nz) - min_abs) / (max_abs - min_abs)
+    eps = 1e-1
+    norm = (np.log(norm + eps) - np.log(eps)) / (np.log(1.0 + eps) - np.log(eps))
+    return _jet_u8(norm)
+
+
+def _read_rendered(path):
+    """binary PCD with FIELDS x y z rgb -> (N x 3 float32, N x 3 uint8)"""
+    raw = open(path, "rb").read()
+    head, data = raw.split(b"DATA binary\n", 1)
+    n = int([l for l in head.decode().splitlines() if l.startswith("POINTS")][0].split()[1])
+    assert "FIELDS x y z rgb" in head.decode()
+    rec = np.frombuffer(data, dtype=np.dtype([("xyz", "<f4", 3), ("rgb", "<u4")]), count=n)
+    rgb = np.stack([(rec["rgb"] >> 16) & 255, (rec["rgb"] >> 8) & 255, rec["rgb"] & 255], axis=1).astype(np.uint8)
+    return rec["xyz"].copy(), rgb
+
+
 @pytest.fixture(scope="module")
 def exe():
     if not os.path.exists(EXE):
@@ -186,6 +218,21 @@ def test_map_eval_end_to_end(exe, tmp_path):
     np.testing.assert_allclose(cdf[:, 0], np.sort(orows[:, 9]), rtol=1e-5)
     np.testing.assert_allclose(cdf[:, 1], (np.arange(len(cdf)) + 1) / len(cdf), rtol=1e-5)
     assert "INFO: Spatial Consistency Score (SCS):" in out.stdout and "MME EST-GT:" in out.stdout
+    # rendered clouds (map_eval.cpp:404-412, 485-499)
+    res_dir = est_dir / "map_results"
+    ent_pts, ent_rgb = _read_rendered(str(res_dir / "map_entropy.pcd"))
+    _, oent = O.eval_mme(est, 0.1, 10, want_entropies=True)
+    assert len(ent_pts) == me.n_valid
+    np.testing.assert_allclose(ent_pts, est[oent != 0].astype(np.float32), rtol=0, atol=0)
+    np.testing.assert_array_equal(ent_rgb, _entropy_colors(oent))
+    gt_pts, _ = _read_rendered(str(res_dir / "gt_entropy.pcd"))
+    assert len(gt_pts) == mg.n_valid
+    raw_pts, raw_rgb = _read_rendered(str(res_dir / "raw_rendered_dis_map.pcd"))
+    _, od2 = O.knn1(est, gt)
+    assert len(raw_pts) == len(est)
+    np.testing.assert_array_equal(raw_rgb, _jet_u8(np.minimum(od2, 0.2) / 0.2))       # squared distance vs accuracy_level[0] (quirk)
+    inl_pts, inl_rgb = _read_rendered(str(res_dir / "inlier_rendered_dis_map.pcd"))
+    assert len(inl_pts) == onn.est_to_gt.n_corr
     # evaluate_using_initial: false with generalized ICP (registration_methods: 2, the shipped default) is not provided
     cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false"))
     out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
