@@ -322,3 +322,8 @@ def test_map_eval_two_gpus_matches_one(exe, tmp_path):
         assert outs[1][key] == outs[2][key], key
     for key in ("RMSE/AC", "MME", "VMD", "SCS"):
         np.testing.assert_allclose([float(x) for x in outs[2][key]], [float(x) for x in outs[1][key]], rtol=1e-12, atol=1e-12, err_msg=key)
+    # the rendered clouds are assembled from the per-GPU shards of the per-point results: byte-identical files
+    for name in ("map_entropy.pcd", "gt_entropy.pcd", "raw_rendered_dis_map.pcd", "inlier_rendered_dis_map.pcd"):
+        a = (tmp_path / "run1" / "est" / "map_results" / name).read_bytes()
+        b = (tmp_path / "run2" / "est" / "map_results" / name).read_bytes()
+        assert len(a) > 200 and a == b, name
