@@ -113,6 +113,15 @@ def _cpu_pass(est, gt, cfg, threads):
     return time.perf_counter() - t0
 
 
+def _host_threads():
+    """All the host threads this process may use.  (Under torchrun OMP_NUM_THREADS is forced to 1 per rank, which
+    omp_get_max_threads() would report; the CPU arm runs on rank 0 alone and takes the cores of the box.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def _cpu_sample(name, target_pts=1_000_000):
     base = synth.CONFIGS[name]
     scale = min(1.0, target_pts / base["n_est"])
@@ -126,7 +135,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.num_threads()
+    threads = _host_threads()
     est, gt, cfg, scale = _cpu_sample(args.config)
     for _ in range(min(args.warmup, 1)):
         _cpu_pass(est, gt, cfg, threads)
@@ -278,7 +287,7 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
-            threads = O.num_threads()
+            threads = _host_threads()
             s_est, s_gt, s_cfg, s_scale = _cpu_sample(args.config)
             dt = _cpu_pass(s_est, s_gt, s_cfg, threads)
             cpu = {"value": len(s_est) / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
