@@ -98,16 +98,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def _cpu_pass(est, gt, cfg, threads):
-    """One full pass with the oracle (the CPU restatement of the reference)."""
+def _cpu_pass(est, gt, cfg, threads, faithful=False):
+    """One full pass with the oracle (the CPU restatement of the reference).  faithful=True keeps the reference's own
+    threading: serial 1-NN loops on path A (map_eval.cpp:1215-1236), TBB / OpenMP for the estimated map's MME
+    (:1716-1717), serial MME of the ground truth (:1451); otherwise every sweep uses all `threads`."""
     from oracle import oracle as O
     p = A.make_nn_params(cfg["tau"], 1.0)
     t0 = time.perf_counter()
-    O.eval_nn(est, gt, p, threads=threads)
+    O.eval_nn(est, gt, p, threads=1 if faithful else threads)
     if cfg["mme"]:
         O.eval_mme(est, cfg["nn_radius"], 10, threads=threads)
         if cfg["gt_mme"]:
-            O.eval_mme(gt, cfg["nn_radius"], 5, threads=threads)
+            O.eval_mme(gt, cfg["nn_radius"], 5, threads=1 if faithful else threads)
     if cfg["awd"]:
         O.eval_awd(est, gt, cfg["vmd_voxel_size"], 100, 5)
     return time.perf_counter() - t0
@@ -142,13 +144,16 @@ def run_reference(args):
     times = [_cpu_pass(est, gt, cfg, threads) for _ in range(args.steps)]
     dt = float(np.mean(times))
     v = len(est) / dt / 1e6
+    dt_f = _cpu_pass(est, gt, cfg, threads, faithful=True)      # SURVEY §8d mode (1), reported next to the headline mode (2)
     sample = f"{args.config} at scale {scale:g} ({len(est)} est vs {len(gt)} gt points, same density), full pass, all-cores mode"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "reference_threading_value": len(est) / dt_f / 1e6,
+                         "reference_threading": "serial 1-NN loops and GT MME as the reference runs them, est MME on all cores"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
