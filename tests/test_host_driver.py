@@ -327,3 +327,21 @@ def test_map_eval_two_gpus_matches_one(exe, tmp_path):
         a = (tmp_path / "run1" / "est" / "map_results" / name).read_bytes()
         b = (tmp_path / "run2" / "est" / "map_results" / name).read_bytes()
         assert len(a) > 200 and a == b, name
+
+
+REF_CONFIG_DIR = "/root/reference/map_eval/config"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIG_DIR), reason="the reference checkout is only present in the authoring container")
+@pytest.mark.parametrize("name", ["config.yaml", "config_building_day.yaml", "config_corridor.yaml", "config_geode.yaml"])
+def test_loader_reads_the_references_shipped_configs(exe, name):
+    """The YAML-subset loader on the configuration files the reference ships (map_eval/config/*.yaml), unmodified."""
+    out, kv = _dump(exe, os.path.join(REF_CONFIG_DIR, name))
+    assert out.returncode == 0, out.stderr
+    assert kv["registration_methods"] == "2" and float(kv["icp_max_distance"]) == 1.0
+    assert [float(x) for x in kv["accuracy_level"].split(",")] == [0.2, 0.1, 0.08, 0.05, 0.01]
+    assert [float(x) for x in kv["initial_matrix"].split(",")][::5] == [1.0, 1.0, 1.0, 1.0]
+    assert float(kv["nn_radius"]) == 0.1 and float(kv["downsample_size"]) == 0.01
+    assert kv["evaluate_using_initial"] == "0" and kv["evaluate_noised_gt"] == "0"       # `evaluate_noise_gt` is not a key the loader reads
+    assert kv["estimate_map_path"].endswith("/") and kv["gt_map_path"].endswith((".pcd", ".ply"))
+    assert float(kv["vmd_voxel_size"]) in (2.0, 3.0)
