@@ -12,7 +12,10 @@ estimated map (and of the GT map when the config says so), per-voxel Gaussians, 
 N > 1 (torchrun, one rank per GPU): the query ranges of the NN and MME sweeps are sharded by rank, both lattices are
 replicated, and the sum-reducible accumulators are all-reduced over NCCL once per step (strong scaling: the cloud
 pair is fixed).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
-`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on the SAME workload as the
+CUDA arm (C3 by default: 10 M vs 10 M); its timed passes are capped by wall time (REF_BUDGET_S) and the line says how
+many ran.  `e2e_pageable` repeats the e2e arm from plain (pageable) numpy memory, the way a std::vector caller hands
+the clouds over.  For N > 1 the e2e arm uploads 1/N of each cloud per rank and all-gathers over NVLink (NCCL).
 """
 import argparse
 import ctypes as C
@@ -131,32 +134,52 @@ def _cpu_sample(name, target_pts=1_000_000):
     return est, gt, cfg, scale
 
 
+REF_BUDGET_S = 200.0      # wall-time cap of the reference arm's timed passes (the driver allows minutes, not hours)
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port: Open3D/Eigen/TBB are absent)."""
+    """--impl reference: the reference's CPU algorithm (oracle port: Open3D/Eigen/TBB are absent) on the same
+    config as the CUDA arm, at full size.  One pass over 10 M vs 10 M points takes the better part of a minute on 128
+    cores, so the number of timed passes is capped by wall time; `steps` is what actually ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
+    from oracle import oracle as O  # noqa: F401
     threads = _host_threads()
-    est, gt, cfg, scale = _cpu_sample(args.config)
-    for _ in range(min(args.warmup, 1)):
-        _cpu_pass(est, gt, cfg, threads)
-    times = [_cpu_pass(est, gt, cfg, threads) for _ in range(args.steps)]
+    est, gt, cfg = synth.make_pair(args.config, scale=args.scale)
+    times = []
+    t_begin = time.perf_counter()
+    for k in range(max(1, args.steps)):
+        times.append(_cpu_pass(est, gt, cfg, threads))
+        if time.perf_counter() - t_begin + times[-1] > REF_BUDGET_S:
+            break
     dt = float(np.mean(times))
     v = len(est) / dt / 1e6
-    dt_f = _cpu_pass(est, gt, cfg, threads, faithful=True)      # SURVEY §8d mode (1), reported next to the headline mode (2)
-    sample = f"{args.config} at scale {scale:g} ({len(est)} est vs {len(gt)} gt points, same density), full pass, all-cores mode"
+    # SURVEY §8d mode (1), the reference's own threading (serial 1-NN loops, serial GT MME): on a 1 M-point sample only —
+    # at full size the serial loops alone take minutes
+    s_est, s_gt, s_cfg, s_scale = _cpu_sample(args.config)
+    dt_f = _cpu_pass(s_est, s_gt, s_cfg, threads, faithful=True)
+    sample = (f"{args.config} at full size ({len(est)} est vs {len(gt)} gt points), full pass, all-cores mode, "
+              f"{len(times)} timed pass(es) of {args.steps} requested (wall-time cap {REF_BUDGET_S:.0f} s), no warm-up pass")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "steps_requested": args.steps, "warmup": 0, "warmup_requested": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "sample": sample},
+        "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "n_est": len(est), "n_gt": len(gt),
+                   "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "reference_threading_value": len(est) / dt_f / 1e6,
-                         "reference_threading": "serial 1-NN loops and GT MME as the reference runs them, est MME on all cores"},
+                         "pass_seconds": times,
+                         "reference_threading_value": len(s_est) / dt_f / 1e6,
+                         "reference_threading": f"serial 1-NN loops and GT MME as the reference runs them, est MME on all cores; "
+                                                f"{args.config} at scale {s_scale:g} ({len(s_est)} points)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def _alloc_pinned(t):
+    return t.pin_memory()
 
 
 def main():
@@ -168,6 +191,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; not a bench line)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arms (large configs on small hosts)")
+    ap.add_argument("--gen", default="auto", choices=["auto", "numpy", "device"],
+                    help="where the synthetic clouds are generated (auto: on the device above 20 M points)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -196,25 +222,60 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start: launch it early
-    est, gt, cfg = synth.make_pair(args.config, scale=args.scale)
-    n_est, n_gt = len(est), len(gt)
+    base = synth.CONFIGS[args.config]
+    gen = args.gen
+    if gen == "auto":
+        gen = "device" if max(base["n_est"], base["n_gt"]) * args.scale > 20_000_000 else "numpy"
+    if gen == "device":
+        from cloud_map_evaluation_b200 import synth_torch
+        d_est, d_gt, cfg = synth_torch.make_pair(args.config, scale=args.scale, device=dev)
+    else:
+        est, gt, cfg = synth.make_pair(args.config, scale=args.scale)
+        d_est = torch.from_numpy(est).to(dev)
+        d_gt = torch.from_numpy(gt).to(dev)
+    n_est, n_gt = d_est.shape[0], d_gt.shape[0]
     p = A.make_nn_params(cfg["tau"], 1.0)        # path A as written + full CD
 
-    # pinned host copies (e2e arm) and device-resident copies (value arm)
-    h_est = torch.from_numpy(est).pin_memory()
-    h_gt = torch.from_numpy(gt).pin_memory()
-    d_est = h_est.to(dev)
-    d_gt = h_gt.to(dev)
+    # host copies for the e2e arms.  N = 1: the whole clouds, pinned (e2e) and pageable (e2e_pageable).  N > 1: every
+    # rank holds 1/N of each cloud on its host side, uploads that slice over its own PCIe link and the slices are
+    # all-gathered over NVLink (NCCL) — the full 480 MB no longer crosses every rank's PCIe link.
+    do_e2e = not args.no_e2e
+    m_est, m_gt = -(-n_est // world), -(-n_gt // world)          # slice lengths (last slice padded)
+    h_est = h_gt = p_est = p_gt = None
+    g_est = g_gt = None
+    if do_e2e:
+        def host_slice(d_full, m):
+            lo, hi = rank * m, min(d_full.shape[0], (rank + 1) * m)
+            h = torch.zeros((m, 3), dtype=torch.float64)
+            if hi > lo:
+                h[:hi - lo] = d_full[lo:hi].cpu()
+            return h
+        if world == 1:
+            h_est, h_gt = d_est.cpu(), d_gt.cpu()
+            p_est, p_gt = h_est.numpy().copy(), h_gt.numpy().copy()        # plain pageable memory
+            h_est, h_gt = _alloc_pinned(h_est), _alloc_pinned(h_gt)
+        else:
+            h_est, h_gt = _alloc_pinned(host_slice(d_est, m_est)), _alloc_pinned(host_slice(d_gt, m_gt))
+            g_est = torch.empty((world * m_est, 3), dtype=torch.float64, device=dev)
+            g_gt = torch.empty((world * m_gt, 3), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
     ctx = api.MapEvalB200(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream,
                           vmd_voxel_size=cfg["vmd_voxel_size"] if cfg["awd"] else 0.0)
 
     results = {}
 
-    def one_pass(host_buffers):
-        if host_buffers:
+    def one_pass(mode):
+        if mode == "pinned" and world == 1:
             ctx.set_cloud_ptr(A.ME_CLOUD_EST, h_est.data_ptr(), n_est, keepalive=h_est)
             ctx.set_cloud_ptr(A.ME_CLOUD_GT, h_gt.data_ptr(), n_gt, keepalive=h_gt)
+        elif mode == "pageable":
+            ctx.set_cloud(A.ME_CLOUD_EST, p_est)
+            ctx.set_cloud(A.ME_CLOUD_GT, p_gt)
+        elif mode == "pinned":
+            for h, g, m, n, which in ((h_est, g_est, m_est, n_est, A.ME_CLOUD_EST), (h_gt, g_gt, m_gt, n_gt, A.ME_CLOUD_GT)):
+                g[rank * m:(rank + 1) * m].copy_(h, non_blocking=True)
+                dist.all_gather_into_tensor(g.view(-1), g[rank * m:(rank + 1) * m].view(-1))
+                ctx.set_cloud_device(which, g.data_ptr(), n, keepalive=g)
         else:
             ctx.set_cloud_device(A.ME_CLOUD_EST, d_est.data_ptr(), n_est, keepalive=d_est)
             ctx.set_cloud_device(A.ME_CLOUD_GT, d_gt.data_ptr(), n_gt, keepalive=d_gt)
@@ -234,7 +295,7 @@ def main():
         results["awd"] = awd
         results["n_far"] = (nn_e.n_far, nn_g.n_far)
 
-    def timed(host_buffers, steps, stage_acc=None):
+    def timed(mode, steps, stage_acc=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -243,7 +304,7 @@ def main():
         t0 = time.time()
         ev0.record(stream)
         for _ in range(steps):
-            one_pass(host_buffers)
+            one_pass(mode)
             if stage_acc is not None:
                 for k, v in ctx.stage_times_ms().items():
                     stage_acc[k] = stage_acc.get(k, 0.0) + v
@@ -260,20 +321,25 @@ def main():
         return ms / steps, ctx.launch_count() - l0, t0, t1
 
     for _ in range(args.warmup):
-        one_pass(False)
+        one_pass("device")
     stage_ms = {}
-    ms_dev, launches, t0, t1 = timed(False, args.steps, stage_ms)
-    for _ in range(min(args.warmup, 2)):
-        one_pass(True)
-    ms_e2e, _, _, t1b = timed(True, args.steps)
-    clocks = sampler.stop(t0, t1b) if sampler else None
+    ms_dev, launches, t0, t1 = timed("device", args.steps, stage_ms)
+    t_last = t1
+    ms_e2e = ms_page = None
+    if do_e2e:
+        for _ in range(min(args.warmup, 2)):
+            one_pass("pinned")
+        ms_e2e, _, _, t_last = timed("pinned", args.steps)
+        if world == 1:
+            one_pass("pageable")
+            ms_page, _, _, t_last = timed("pageable", max(1, min(args.steps, 5)))
+    clocks = sampler.stop(t0, t_last) if sampler else None
 
     if rank == 0:
         stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
         value = n_est / (ms_dev * 1e-3) / 1e6
-        e2e = n_est / (ms_e2e * 1e-3) / 1e6
         peak, peak_src = _peaks()
-        # dominant kernel: the MME radius sweep of the estimated map (stage "mme_est" = mme_flat_kernel + a 1-thread init).
+        # dominant kernel: the MME radius sweep of the estimated map (stage "mme_est" = the sweep kernel + a 1-thread init).
         # algorithmic bytes per launch: 12 B query + 12 B reference + 8 B entropy out per point of this
         # rank's query range
         nq = n_est * (rank + 1) // world - n_est * rank // world
@@ -282,16 +348,31 @@ def main():
         dom_ms = stage_ms.get(dom, 0.0)
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
         traffic = _profile_traffic()
-        roofline = {"bound": "hbm", "kernel": "mme_flat_kernel" if cfg["mme"] else "nn_flat_kernel",
+        same_cfg = bool(traffic) and args.config == "C3" and args.scale == 1.0 and world == 1
+        roofline = {"bound": "hbm", "kernel": (traffic or {}).get("kernel_name", "mme sweep" if cfg["mme"] else "nn sweep"),
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
-                    "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                    "note": "neighbour sweep bound by issue slots and L1/L2 latency (~137 candidate tests per query served "
-                            "from cache); the HBM fraction is small by construction (SURVEY §8d, DESIGN §3)"}
+                    "traffic": traffic.get("dram_bytes_per_launch") if same_cfg else None,
+                    "note": "neighbour sweep bound by issue slots and L1/L2 latency (~130 candidate tests per query served "
+                            "from cache / shared memory); the HBM fraction is small by construction (SURVEY §8d, DESIGN §3)"}
+        # the resource that actually binds the sweep: warp-instruction issue slots (4 schedulers x 1 instruction per
+        # clock per SM).  Instruction, candidate-test and accepted-pair counts per launch come from the committed ncu
+        # capture of this kernel on this config (profiles/roofline_traffic.json); the time is this run's.
+        binding = None
+        if same_cfg and dom_ms > 0 and traffic.get("warp_inst_per_launch"):
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            issue_peak = 148 * 4 * sm_mhz * 1e6
+            wi = float(traffic["warp_inst_per_launch"])
+            binding = {"resource": "warp-instruction issue slots", "achieved": wi / (dom_ms * 1e-3), "peak": issue_peak,
+                       "unit": "warp-inst/s", "frac": wi / (dom_ms * 1e-3) / issue_peak,
+                       "candidate_tests_per_s": float(traffic.get("candidate_tests_per_launch", 0)) / (dom_ms * 1e-3),
+                       "accepted_pairs_per_s": float(traffic.get("accepted_pairs_per_launch", 0)) / (dom_ms * 1e-3),
+                       "thread_inst_per_warp_inst": traffic.get("thread_inst_per_warp_inst"),
+                       "source": traffic.get("source")}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle as O
+            from oracle import oracle as O  # noqa: F401
             threads = _host_threads()
             s_est, s_gt, s_cfg, s_scale = _cpu_sample(args.config)
             dt = _cpu_pass(s_est, s_gt, s_cfg, threads)
@@ -299,6 +380,14 @@ def main():
                    "sample": f"{args.config} at scale {s_scale:g} ({len(s_est)} est vs {len(s_gt)} gt points, same "
                              f"density), one full pass in {dt:.1f} s, all-cores mode"}
         nn = results["nn"]
+        d2h = (2 * C.sizeof(A.me_nn_accum) + C.sizeof(A.me_mme_accum) * len(results["mme"]) + C.sizeof(A.me_awd_result))
+        e2e = None
+        if ms_e2e:
+            e2e = {"value": n_est / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": 24 * (m_est + m_gt) if world > 1 else 24 * (n_est + n_gt),
+                   "d2h_bytes_per_step": d2h,
+                   "host_memory": "pinned" if world == 1 else
+                   f"pinned; each rank uploads 1/{world} of both clouds, slices all-gathered over NVLink (NCCL) inside the timed region"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
@@ -306,23 +395,31 @@ def main():
             "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "n_est": n_est,
                        "n_gt": n_gt, "tau": cfg["tau"], "icp_max_distance": 1.0, "nn_radius": cfg["nn_radius"],
                        "vmd_voxel_size": cfg["vmd_voxel_size"], "mme_gt": bool(cfg["gt_mme"]),
+                       "generated": gen,
                        "parallelism": f"query-range shard x{world}, lattices replicated",
-                       "l2": "inputs per pass (2 x 240 MB fp64 clouds, 2 x 320 MB sorted records, 2 x 160 MB fp32 screening copies) "
-                             "exceed the 126 MB L2 several times over; no flush needed"},
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 24 * (n_est + n_gt),
-                    "d2h_bytes_per_step": 2 * C.sizeof(A.me_nn_accum) + C.sizeof(A.me_mme_accum) * len(results["mme"])
-                    + C.sizeof(A.me_awd_result)},
+                       "l2": f"inputs per pass ({24 * (n_est + n_gt) / 1e6:.0f} MB of fp64 clouds, {48 * (n_est + n_gt) / 1e6:.0f} MB of "
+                             "sorted records and fp32 screening copies) exceed the 126 MB L2 several times over; no flush needed"},
+            "e2e": e2e,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "stage_ms": stage_ms,
             "check": {"AC_rmse": list(nn.est_to_gt.rmse), "n_inlier": list(nn.est_to_gt.n_inlier),
+                      "n_inlier_gt_to_est": list(nn.gt_to_est.n_inlier), "n_corr": [nn.est_to_gt.n_corr, nn.gt_to_est.n_corr],
                       "full_cd": nn.full_cd, "mme": [m.mme for m in results["mme"]],
+                      "mme_n_valid": [m.n_valid for m in results["mme"]],
                       "awd": results["awd"].awd if results["awd"] else None,
-                      "scs": results["awd"].scs if results["awd"] else None, "n_far": list(results["n_far"])},
+                      "scs": results["awd"].scs if results["awd"] else None,
+                      "awd_n_pairs": results["awd"].n_pairs if results["awd"] else None, "n_far": list(results["n_far"])},
         }
+        if binding:
+            line["roofline_binding"] = binding
+        if ms_page:
+            line["e2e_pageable"] = {"value": n_est / (ms_page * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_page,
+                                    "h2d_bytes_per_step": 24 * (n_est + n_gt), "d2h_bytes_per_step": d2h,
+                                    "host_memory": "pageable (plain numpy arrays handed to me_set_cloud, the way a "
+                                                   "std::vector<Eigen::Vector3d> caller does)"}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:

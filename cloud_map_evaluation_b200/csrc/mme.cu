@@ -275,6 +275,169 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// rows kernel (rings <= 3): warp-synchronous row walk with deferred fp64 accumulation.
+//
+// Same decomposition as the flat kernel (one thread per query, queries in cell-sorted order, the (2R+1)^2 lattice rows
+// pruned against the sphere), but the control flow is WARP-UNIFORM: the rows are enumerated by a compile-time loop that
+// all 32 lanes run together, and inside a row every lane walks its own x-run for max-over-lanes(len) steps
+// (REDUX.MAX).  No run table, no per-lane refill branches: at any time the 32 lanes read the same row of the reference
+// cloud, i.e. a window of a few consecutive 128-byte lines (the flat walk has its lanes in up to 27 different rows at
+// once).  The price is lanes idling while the longest run of the row finishes (~50 % of the slots on C3).
+//
+// The fp64 work is taken off the walk: a candidate that passes the fp32 screen (d2 < r2_hi) is only APPENDED — one
+// predicated STS.128 of (dx, dy, dz, index) to a per-thread ring in shared memory ([slot][thread], conflict-free).
+// When some lane's ring is nearly full the warp drains all rings together: a dense loop in which ~3 of 4 lanes hold an
+// entry, where the exact fp64 decision inside the error band (rare) and the 12 fp64 moment updates run.  In the flat
+// kernel those 16 fp64-pipe instructions were issued at every step for the ~40 % of lanes that accept.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kRowsThreads = 128;
+
+// shared-memory ring accessed through 32-bit shared addresses held in one register (the compiler otherwise rebuilds the
+// generic pointer from %tid at every store)
+__device__ __forceinline__ void ring_put(uint32_t addr, float a, float b, float c, uint32_t d, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}\n"
+               ::"r"(addr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(d), "r"((uint32_t)p));
+}
+__device__ __forceinline__ uint4 ring_get(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int R, int CAP, int U>      // CAP ring slots per thread, U candidates per inner iteration
+__global__ void __launch_bounds__(kRowsThreads, (R <= 2 ? 6 : 5))
+mme_rows_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
+                const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
+                MmeAcc *__restrict__ acc) {
+  constexpr int NS = 2 * R + 1;
+  constexpr uint32_t kSlot = kRowsThreads * sizeof(uint4);      // bytes between two slots of one thread
+  extern __shared__ __align__(16) unsigned char rows_smem[];
+  // slot t of this thread: ring0 + t * kSlot
+  uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(rows_smem) + threadIdx.x * (uint32_t)sizeof(uint4);
+  asm volatile("" : "+r"(ring0));      // opaque: keep it in a register
+  // per-thread squared gaps (in cells) to the lattice rows dy / planes dz away: gyz[dy + R][thread], gyz[NS + dz + R][thread]
+  float *gyz = reinterpret_cast<float *>(rows_smem + (size_t)CAP * kSlot) + threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  const float h = C.h, r2_lo = C.r2_lo, r2_hi = C.r2_hi;
+  ThreadStats ts;
+  ts.init();
+  const long long stride = (long long)gridDim.x * kRowsThreads;
+  for (long long base = q_begin + blockIdx.x * (long long)kRowsThreads; base < q_end; base += stride) {
+    const long long i = base + threadIdx.x;
+    const bool live = i < q_end;                      // dead lanes run along with empty runs (warp collectives need them)
+    const long long il = live ? i : q_end - 1;
+    const float4 qr = __ldg(rel + il);
+    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + il) + 3)));
+    const int ix = (int)qr.w;
+    const uint32_t cyz = cq / (uint32_t)C.dimx;
+    const int iy = (int)(cyz % (uint32_t)C.dimy), iz = live ? (int)(cyz / (uint32_t)C.dimy) : -1000000;
+    const float ux = qr.x * C.inv_h;
+    {
+      const float uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
+#pragma unroll
+      for (int d = -R; d <= R; ++d) { gyz[(d + R) * kRowsThreads] = gap2(d, uy); gyz[(NS + d + R) * kRowsThreads] = gap2(d, uz); }
+    }
+
+    Moments m;
+    m.init();
+    uint32_t wp = ring0;                               // next free slot of this thread's ring
+    // drain the rings of the whole warp: exact decision inside the fp32 error band, then the fp64 moments
+    auto drain = [&]() {
+      const uint32_t mx = __reduce_max_sync(FULL, wp - ring0);
+#pragma unroll 1
+      for (uint32_t t = 0; t < mx; t += kSlot) {
+        if (ring0 + t < wp) {
+          const uint4 v = ring_get(ring0 + t);
+          const float dx = __uint_as_float(v.x), dy = __uint_as_float(v.y), dz = __uint_as_float(v.z);
+          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          bool in = true;
+          if (d2 > r2_lo) {
+            const P4 q = load_p4(S + i), p = load_p4(S + v.w);
+            in = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z) < C.r2;      // nanoflann RadiusResultSet: strict <
+          }
+          if (in) m.add((double)dx, (double)dy, (double)dz);
+        }
+      }
+      wp = ring0;
+    };
+
+    // the (2R+1)^2 rows, one after the other for the whole warp (a runtime loop: one copy of the walk in the instruction
+    // cache instead of 25)
+    int dy = -R, dz = -R;
+#pragma unroll 1
+    for (int row_i = 0; row_i < NS * NS; ++row_i) {
+      const int z = iz + dz, y = iy + dy;
+      const float rem = C.rc2 - gyz[(NS + dz + R) * kRowsThreads] - gyz[(dy + R) * kRowsThreads];
+      uint32_t s = 0, e = 0;
+      if ((unsigned)z < (unsigned)C.dimz && (unsigned)y < (unsigned)C.dimy && rem >= 0.f) {
+        // cells d steps to the left have gap ux + d - 1, to the right d - ux: keep those with gap <= sqrt(rem) (+ slack)
+        const float xw = sqrt_approx(rem) + 1e-3f;
+        const int da = min(R, (int)(xw - ux + 1.f)), db = min(R, (int)(xw + ux));
+        const int xa = max(ix - da, 0), xb = min(ix + db, C.dimx - 1);
+        const uint32_t row = ((uint32_t)z * (uint32_t)C.dimy + (uint32_t)y) * (uint32_t)C.dimx;
+        s = __ldg(cell_off + row + xa);
+        e = __ldg(cell_off + row + xb + 1);
+      }
+      const int len = (int)(e - s);
+      const int maxlen = __reduce_max_sync(FULL, len);
+      const float cyv = (float)dy * h - qr.y, czv = (float)dz * h - qr.z;
+      const float4 *p = rel + s;
+      uint32_t j = s;
+      float4 c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int k0 = 0; k0 < maxlen; k0 += U, p += U, j += U) {
+        if (__any_sync(FULL, wp > ring0 + (uint32_t)(CAP - U) * kSlot)) drain();
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (k0 + u < len) c[u] = __ldg(p + u);       // lanes past their run keep a stale candidate; `take` masks it
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float dx = fmaf(c[u].w - qr.w, h, c[u].x - qr.x), dyf = c[u].y + cyv, dzf = c[u].z + czv;
+          const float d2 = fmaf(dzf, dzf, fmaf(dyf, dyf, dx * dx));
+          const bool take = (k0 + u < len) && (d2 < r2_hi);
+          ring_put(wp, dx, dyf, dzf, j + (uint32_t)u, take);
+          wp += take ? kSlot : 0u;
+        }
+      }
+      if (++dy > R) { dy = -R; ++dz; }
+    }
+    drain();
+    const double ent = finish_entropy(m, C.min_neighbors, ts);
+    if (live) entropy_sorted[i] = ent;
+    else ts.queries--;       // finish_entropy counted the dead lane
+  }
+  flush_stats(ts, acc);
+}
+
+template <int R, int CAP, int U>
+static int launch_rows_v(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
+  const size_t smem = (size_t)CAP * kRowsThreads * sizeof(uint4) + (size_t)2 * (2 * R + 1) * kRowsThreads * sizeof(float);
+  if (smem > 48 * 1024)
+    ME_CUDA(ctx, cudaFuncSetAttribute(mme_rows_kernel<R, CAP, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = (int)std::min<long long>((qe - qb + kRowsThreads - 1) / kRowsThreads, (long long)ctx->sm_count * 192);
+  mme_rows_kernel<R, CAP, U><<<blocks, kRowsThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, c.d_entropy, acc);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
+template <int R>
+static int launch_rows(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, MmeAcc *acc) {
+  const char *v = getenv("ME_MME_ROWS");      // tuning hook: ring capacity / candidates per iteration
+  if (v && !strcmp(v, "8,2")) return launch_rows_v<R, 8, 2>(ctx, c, qb, qe, C, acc);
+  if (v && !strcmp(v, "16,2")) return launch_rows_v<R, 16, 2>(ctx, c, qb, qe, C, acc);
+  if (v && !strcmp(v, "12,4")) return launch_rows_v<R, 12, 4>(ctx, c, qb, qe, C, acc);
+  if (v && !strcmp(v, "16,4")) return launch_rows_v<R, 16, 4>(ctx, c, qb, qe, C, acc);
+  return launch_rows_v<R, 12, 2>(ctx, c, qb, qe, C, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // plane kernel (3 < rings <= kMaxPlaneRings): the same fp32-screened walk for radii spanning many cells (e.g. r = 1.0 m
 // on a ~0.15 m lattice).  The run table holds the 2R+1 rows of ONE dz plane at a time (a full (2R+1)^2 table would not
 // fit), the candidates of a plane are walked flattened, lanes re-synchronise at the plane boundaries — cheap here,
@@ -451,7 +614,14 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
       C.r2_hi = (float)((C.r2 + band) * (1.0 + 1e-7));
       C.min_neighbors = min_neighbors;
       C.dimx = c.lat.dims[0]; C.dimy = c.lat.dims[1]; C.dimz = c.lat.dims[2];
-      if (rings == 1) ME_TRY(launch_flat<1>(ctx, c, qb, qe, C, acc));
+      const char *kv = getenv("ME_MME_KERNEL");          // test hook: "flat" = the round-1 run-table walk
+      const bool use_flat = kv && !strcmp(kv, "flat");
+      if (rings <= 3 && !use_flat) {
+        if (rings == 1) ME_TRY(launch_rows<1>(ctx, c, qb, qe, C, acc));
+        else if (rings == 2) ME_TRY(launch_rows<2>(ctx, c, qb, qe, C, acc));
+        else ME_TRY(launch_rows<3>(ctx, c, qb, qe, C, acc));
+      }
+      else if (rings == 1) ME_TRY(launch_flat<1>(ctx, c, qb, qe, C, acc));
       else if (rings == 2) ME_TRY(launch_flat<2>(ctx, c, qb, qe, C, acc));
       else if (rings == 3) ME_TRY(launch_flat<3>(ctx, c, qb, qe, C, acc));
       else ME_TRY(launch_plane(ctx, c, qb, qe, C, rings, acc));

@@ -127,6 +127,34 @@ struct KdTree {
     if (dsecond * dsecond <= bd) knn1_rec(second, q, bi, bd);
   }
 
+  // k nearest neighbours, ascending distance [ext-kd: nanoflann KNNResultSet keeps its list sorted; entries of equal
+  // distance stay in insertion order there, i.e. traversal order — restated as "smaller index first"]
+  void knn(const double *q, int k, std::vector<std::pair<double, int32_t>> &out) const {
+    out.clear();
+    if (n == 0 || k <= 0) return;
+    knn_rec(0, q, k, out);
+  }
+  void knn_rec(int32_t id, const double *q, int k, std::vector<std::pair<double, int32_t>> &out) const {
+    const Node &nd = nodes[id];
+    if (nd.left < 0) {
+      for (int32_t i = nd.begin; i < nd.end; ++i) {
+        const int32_t j = idx[i];
+        const std::pair<double, int32_t> c(d2_kd(q, pts + 3 * (int64_t)j), j);
+        if ((int)out.size() == k && !(c < out.back())) continue;
+        out.insert(std::upper_bound(out.begin(), out.end(), c), c);
+        if ((int)out.size() > k) out.pop_back();
+      }
+      return;
+    }
+    const double v = q[nd.dim];
+    const double dl = v > nd.split_lo ? v - nd.split_lo : 0.0;
+    const double dr = v < nd.split_hi ? nd.split_hi - v : 0.0;
+    int32_t first = nd.left, second = nd.right; double dsecond = dr;
+    if (dr < dl) { first = nd.right; second = nd.left; dsecond = dl; }
+    knn_rec(first, q, k, out);
+    if ((int)out.size() < k || dsecond * dsecond <= out.back().first) knn_rec(second, q, k, out);
+  }
+
   // all points with d2 < r2 (strict) [ext-kd]
   void radius(const double *q, double r2, std::vector<std::pair<double, int32_t>> &out) const {
     out.clear();
@@ -841,6 +869,332 @@ int oracle_icp_point_to_point(const double *est, int64_t n_est, const double *gt
   std::memcpy(T_out, T, sizeof(T));
   *fitness = res.fitness; *inlier_rmse = res.rmse; *n_corr = res.n_corr; *iterations = it;
   return 0;
+}
+
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// [ext-gicp] MapEval::performICPRegistration cases 1 and 2 (map_eval.cpp:1375-1386): Open3D's point-to-plane ICP and
+// RegistrationGeneralizedICP with TransformationEstimationForGeneralizedICP() (epsilon = 1e-3) and the default
+// convergence criteria.  Open3D 0.15-0.17 (not vendored), restated from its published sources:
+//   GeneralizedICP.cpp  InitializePointCloudForGeneralizedICP: no covariances, no normals ->
+//                         EstimateNormals(KDTreeSearchParamKNN(20)); covariance_i = Rx diag(eps, 1, 1) Rx^T with
+//                         Rx = GetRotationFromE1ToX(normal_i) = I + [v]x + [v]x^2 / (1 + c), v = e1 x n, c = e1 . n,
+//                         and Rx = I when c < -0.99 (sic)
+//                       ComputeTransformation: per pair d = vs - vt, M = Ct + Cs, W = M^-1/2, J = W [-skew(vs) | I],
+//                         r = W d; JTJ = sum J^T J, JTr = sum J^T r; x = solve(JTJ, -JTr) (LDLT);
+//                         update = TransformVector6dToMatrix4d(x) = Rz(x2) Ry(x1) Rx(x0), t = x[3..5]
+//   EstimateNormals.cpp EstimatePerPointCovariances: KNN(20) incl. the point itself, >= 3 neighbours else identity;
+//                         utility::ComputeCovariance: cumulants of the RAW coordinates / k, cov = E[xy] - E[x]E[y];
+//                         ComputeNormal(fast): FastEigen3x3 = Eberly's robust 3x3 symmetric eigen-solver, eigenvector of
+//                         the smallest eigenvalue; zero vector -> (0, 0, 1)
+//   PointCloud::Transform also rotates normals and covariances (R C R^T)
+//   TransformationEstimationPointToPlane::ComputeTransformation: r = (vs - vt) . nt, J = [vs x nt, nt]
+//   Registration.cpp    RegistrationICP loop as in [ext-icp] above; fitness / inlier_rmse are the point-to-point
+//                         quantities of GetRegistrationResultAndCorrespondences for every estimation type
+// Parity unpinned: the reference holds no registration fixtures; tests/test_oracle_icp.py checks this restatement
+// against an independent numpy / scipy statement of the same equations.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+void cross3(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+double dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// Eberly, "A Robust Eigensolver for 3x3 Symmetric Matrices" (Open3D FastEigen3x3): unit eigenvector for eval0 of A
+void eberly_evec0(const double A[9], double eval0, double out[3]) {
+  const double row0[3] = {A[0] - eval0, A[1], A[2]}, row1[3] = {A[1], A[4] - eval0, A[5]}, row2[3] = {A[2], A[5], A[8] - eval0};
+  double r0xr1[3], r0xr2[3], r1xr2[3];
+  cross3(row0, row1, r0xr1); cross3(row0, row2, r0xr2); cross3(row1, row2, r1xr2);
+  const double d0 = dot3(r0xr1, r0xr1), d1 = dot3(r0xr2, r0xr2), d2 = dot3(r1xr2, r1xr2);
+  double dmax = d0; int imax = 0;
+  if (d1 > dmax) { dmax = d1; imax = 1; }
+  if (d2 > dmax) imax = 2;
+  const double *v = imax == 0 ? r0xr1 : (imax == 1 ? r0xr2 : r1xr2);
+  const double s = std::sqrt(imax == 0 ? d0 : (imax == 1 ? d1 : d2));
+  for (int k = 0; k < 3; ++k) out[k] = v[k] / s;
+}
+void eberly_evec1(const double A[9], const double evec0[3], double eval1, double out[3]) {
+  double U[3], V[3];
+  if (std::fabs(evec0[0]) > std::fabs(evec0[1])) {
+    const double inv = 1.0 / std::sqrt(evec0[0] * evec0[0] + evec0[2] * evec0[2]);
+    U[0] = -evec0[2] * inv; U[1] = 0; U[2] = evec0[0] * inv;
+  } else {
+    const double inv = 1.0 / std::sqrt(evec0[1] * evec0[1] + evec0[2] * evec0[2]);
+    U[0] = 0; U[1] = evec0[2] * inv; U[2] = -evec0[1] * inv;
+  }
+  cross3(evec0, U, V);
+  const double AU[3] = {A[0] * U[0] + A[1] * U[1] + A[2] * U[2], A[1] * U[0] + A[4] * U[1] + A[5] * U[2], A[2] * U[0] + A[5] * U[1] + A[8] * U[2]};
+  const double AV[3] = {A[0] * V[0] + A[1] * V[1] + A[2] * V[2], A[1] * V[0] + A[4] * V[1] + A[5] * V[2], A[2] * V[0] + A[5] * V[1] + A[8] * V[2]};
+  double m00 = dot3(U, AU) - eval1, m01 = dot3(U, AV), m11 = dot3(V, AV) - eval1;
+  const double a00 = std::fabs(m00), a01 = std::fabs(m01), a11 = std::fabs(m11);
+  if (a00 >= a11) {
+    if (std::max(a00, a01) > 0) {
+      if (a00 >= a01) { m01 /= m00; m00 = 1 / std::sqrt(1 + m01 * m01); m01 *= m00; }
+      else { m00 /= m01; m01 = 1 / std::sqrt(1 + m00 * m00); m00 *= m01; }
+      for (int k = 0; k < 3; ++k) out[k] = m01 * U[k] - m00 * V[k];
+    } else for (int k = 0; k < 3; ++k) out[k] = U[k];
+  } else {
+    if (std::max(a11, a01) > 0) {
+      if (a11 >= a01) { m01 /= m11; m11 = 1 / std::sqrt(1 + m01 * m01); m01 *= m11; }
+      else { m11 /= m01; m01 = 1 / std::sqrt(1 + m11 * m11); m11 *= m01; }
+      for (int k = 0; k < 3; ++k) out[k] = m11 * U[k] - m01 * V[k];
+    } else for (int k = 0; k < 3; ++k) out[k] = U[k];
+  }
+}
+// Open3D ComputeNormal(covariance, fast_normal_computation = true): eigenvector of the smallest eigenvalue
+void fast_eigen3x3_normal(const double cov[9], double nrm[3]) {
+  double A[9];
+  double max_coeff = cov[0];
+  for (int k = 1; k < 9; ++k) max_coeff = std::max(max_coeff, cov[k]);
+  if (max_coeff == 0) { nrm[0] = nrm[1] = nrm[2] = 0; return; }
+  for (int k = 0; k < 9; ++k) A[k] = cov[k] / max_coeff;
+  const double norm = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+  if (norm > 0) {
+    const double q = (A[0] + A[4] + A[8]) / 3;
+    const double b00 = A[0] - q, b11 = A[4] - q, b22 = A[8] - q;
+    const double p = std::sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2) / 6);
+    const double c00 = b11 * b22 - A[5] * A[5], c01 = A[1] * b22 - A[5] * A[2], c02 = A[1] * A[5] - b11 * A[2];
+    const double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
+    const double half_det = std::min(std::max(det * 0.5, -1.0), 1.0);
+    const double angle = std::acos(half_det) / 3.0;
+    const double two_thirds_pi = 2.09439510239319549;
+    const double beta2 = std::cos(angle) * 2, beta0 = std::cos(angle + two_thirds_pi) * 2, beta1 = -(beta0 + beta2);
+    const double ev[3] = {q + p * beta0, q + p * beta1, q + p * beta2};
+    double e0[3], e1[3], e2[3];
+    if (half_det >= 0) {
+      eberly_evec0(A, ev[2], e2);
+      if (ev[2] < ev[0] && ev[2] < ev[1]) { for (int k = 0; k < 3; ++k) nrm[k] = e2[k]; return; }
+      eberly_evec1(A, e2, ev[1], e1);
+      if (ev[1] < ev[0] && ev[1] < ev[2]) { for (int k = 0; k < 3; ++k) nrm[k] = e1[k]; return; }
+      cross3(e1, e2, nrm);
+    } else {
+      eberly_evec0(A, ev[0], e0);
+      if (ev[0] < ev[1] && ev[0] < ev[2]) { for (int k = 0; k < 3; ++k) nrm[k] = e0[k]; return; }
+      eberly_evec1(A, e0, ev[1], e1);
+      if (ev[1] < ev[0] && ev[1] < ev[2]) { for (int k = 0; k < 3; ++k) nrm[k] = e1[k]; return; }
+      cross3(e0, e1, nrm);
+    }
+  } else {
+    nrm[0] = nrm[1] = nrm[2] = 0;
+    if (cov[0] < cov[4] && cov[0] < cov[8]) nrm[0] = 1;
+    else if (cov[4] < cov[0] && cov[4] < cov[8]) nrm[1] = 1;
+    else nrm[2] = 1;
+  }
+}
+
+// PointCloud::EstimateNormals(KDTreeSearchParamKNN(knn)) on a cloud without normals / covariances
+void estimate_normals_knn(const double *xyz, int64_t n, int knn, std::vector<double> &normals) {
+  KdTree tree;
+  tree.build(xyz, n);
+  normals.assign((size_t)3 * n, 0.0);
+#pragma omp parallel
+  {
+    std::vector<std::pair<double, int32_t>> nb;
+#pragma omp for schedule(dynamic, 2048)
+    for (int64_t i = 0; i < n; ++i) {
+      tree.knn(xyz + 3 * i, knn, nb);
+      double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      if (nb.size() >= 3) {
+        double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (const auto &e : nb) {
+          const double *p = xyz + 3 * (int64_t)e.second;
+          c[0] += p[0]; c[1] += p[1]; c[2] += p[2];
+          c[3] += p[0] * p[0]; c[4] += p[0] * p[1]; c[5] += p[0] * p[2];
+          c[6] += p[1] * p[1]; c[7] += p[1] * p[2]; c[8] += p[2] * p[2];
+        }
+        for (int k = 0; k < 9; ++k) c[k] /= (double)nb.size();
+        cov[0] = c[3] - c[0] * c[0]; cov[4] = c[6] - c[1] * c[1]; cov[8] = c[8] - c[2] * c[2];
+        cov[1] = cov[3] = c[4] - c[0] * c[1]; cov[2] = cov[6] = c[5] - c[0] * c[2]; cov[5] = cov[7] = c[7] - c[1] * c[2];
+      }
+      double nr[3];
+      fast_eigen3x3_normal(cov, nr);
+      if (std::sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]) == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+      for (int k = 0; k < 3; ++k) normals[3 * i + k] = nr[k];
+    }
+  }
+}
+
+void mat3_mul(const double a[9], const double b[9], double o[9]) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) o[r * 3 + c] = a[r * 3] * b[c] + a[r * 3 + 1] * b[3 + c] + a[r * 3 + 2] * b[6 + c];
+}
+// GetRotationFromE1ToX(x) diag(eps, 1, 1) GetRotationFromE1ToX(x)^T
+void gicp_covariance(const double x[3], double eps, double cov[9]) {
+  double Rx[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const double v[3] = {0.0, -x[2], x[1]};            // e1 x x
+  const double c = x[0];
+  if (!(c < -0.99)) {
+    const double sv[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+    double sv2[9];
+    mat3_mul(sv, sv, sv2);
+    const double f = 1 / (1 + c);
+    for (int k = 0; k < 9; ++k) Rx[k] += sv[k] + sv2[k] * f;
+  }
+  const double C[9] = {eps, 0, 0, 0, 1, 0, 0, 0, 1};
+  double t[9], RxT[9];
+  for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) RxT[r * 3 + cc] = Rx[cc * 3 + r];
+  mat3_mul(Rx, C, t);
+  mat3_mul(t, RxT, cov);
+}
+
+// solve the symmetric 6x6 system A x = b (Eigen: A.ldlt().solve(b)); Gaussian elimination with partial pivoting
+bool solve6(const double A_in[36], const double b_in[6], double x[6]) {
+  double A[36], b[6];
+  std::memcpy(A, A_in, sizeof(A)); std::memcpy(b, b_in, sizeof(b));
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 6; ++r) if (std::fabs(A[r * 6 + c]) > std::fabs(A[piv * 6 + c])) piv = r;
+    if (A[piv * 6 + c] == 0.0) return false;
+    if (piv != c) { for (int k = 0; k < 6; ++k) std::swap(A[c * 6 + k], A[piv * 6 + k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < 6; ++r) {
+      const double f = A[r * 6 + c] / A[c * 6 + c];
+      for (int k = c; k < 6; ++k) A[r * 6 + k] -= f * A[c * 6 + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = 5; r >= 0; --r) {
+    double s2 = b[r];
+    for (int k = r + 1; k < 6; ++k) s2 -= A[r * 6 + k] * x[k];
+    x[r] = s2 / A[r * 6 + r];
+  }
+  for (int k = 0; k < 6; ++k) if (!std::isfinite(x[k])) return false;
+  return true;
+}
+// utility::TransformVector6dToMatrix4d
+void vec6_to_mat4(const double x[6], double T[16]) {
+  const double ca = std::cos(x[0]), sa = std::sin(x[0]), cb = std::cos(x[1]), sb = std::sin(x[1]), cg = std::cos(x[2]), sg = std::sin(x[2]);
+  const double Rx[9] = {1, 0, 0, 0, ca, -sa, 0, sa, ca}, Ry[9] = {cb, 0, sb, 0, 1, 0, -sb, 0, cb}, Rz[9] = {cg, -sg, 0, sg, cg, 0, 0, 0, 1};
+  double t[9], R[9];
+  mat3_mul(Rz, Ry, t);
+  mat3_mul(t, Rx, R);
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[r * 4 + c] = R[r * 3 + c]; T[r * 4 + 3] = x[3 + r]; }
+  T[12] = T[13] = T[14] = 0; T[15] = 1;
+}
+// W = M^-1/2 of a symmetric positive definite 3x3 (Eigen: M.inverse().sqrt()), through the eigen-decomposition
+void inv_sqrt_spd3(const double M[9], double W[9]) {
+  double w[3], V[9];
+  eig3_jacobi(M, w, V);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double s2 = 0;
+      for (int k = 0; k < 3; ++k) s2 += V[r * 3 + k] * V[c * 3 + k] / std::sqrt(w[k]);
+      W[r * 3 + c] = s2;
+    }
+}
+void rotate_covs(std::vector<double> &c, const double T[16]) {         // PointCloud::TransformCovariances: R C R^T
+  const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  double Rt[9], t[9], o[9];
+  for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) Rt[r * 3 + cc] = R[cc * 3 + r];
+  for (size_t i = 0; i + 8 < c.size(); i += 9) {
+    mat3_mul(R, &c[i], t);
+    mat3_mul(t, Rt, o);
+    std::memcpy(&c[i], o, sizeof(o));
+  }
+}
+
+// method 1: point-to-plane (needs target normals); method 2: generalized ICP
+int icp_normal_equations(int method, const double *est, int64_t n_est, const double *gt, int64_t n_gt,
+                         const double *gt_normals_in, double max_dist, int max_iter, double rel_fitness, double rel_rmse,
+                         const double T_init[16], double T_out[16], double *fitness, double *inlier_rmse, int64_t *n_corr,
+                         int32_t *iterations) {
+  const double eps = 1e-3;
+  KdTree tree;
+  tree.build(gt, n_gt);
+  std::vector<double> pcd(est, est + 3 * n_est), src_cov, tgt_cov, tgt_nrm;
+  if (method == 2) {
+    std::vector<double> ns, nt;
+    estimate_normals_knn(est, n_est, 20, ns);
+    estimate_normals_knn(gt, n_gt, 20, nt);
+    src_cov.resize((size_t)9 * n_est); tgt_cov.resize((size_t)9 * n_gt);
+    for (int64_t i = 0; i < n_est; ++i) gicp_covariance(&ns[3 * i], eps, &src_cov[9 * i]);
+    for (int64_t i = 0; i < n_gt; ++i) gicp_covariance(&nt[3 * i], eps, &tgt_cov[9 * i]);
+  } else {
+    if (!gt_normals_in) return -1;      // Open3D: "requires pre-computed normal vectors for target PointCloud"
+    tgt_nrm.assign(gt_normals_in, gt_normals_in + 3 * n_gt);
+  }
+  double T[16];
+  std::memcpy(T, T_init, sizeof(T));
+  oracle_transform(pcd.data(), n_est, T);
+  if (method == 2) rotate_covs(src_cov, T);
+  IcpEval res, backup;
+  icp_evaluate(tree, pcd.data(), n_est, max_dist, res);
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    double JTJ[36], JTr[6];
+    std::memset(JTJ, 0, sizeof(JTJ)); std::memset(JTr, 0, sizeof(JTr));
+    for (int64_t i = 0; i < n_est; ++i) {
+      if (!res.keep[i]) continue;
+      const double *vs = &pcd[3 * i], *vt = gt + 3ll * res.idx[i];
+      const double d[3] = {vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2]};
+      if (method == 2) {
+        double M[9], W[9];
+        for (int k = 0; k < 9; ++k) M[k] = tgt_cov[9ll * res.idx[i] + k] + src_cov[9 * i + k];
+        inv_sqrt_spd3(M, W);
+        const double A[18] = {0, vs[2], -vs[1], 1, 0, 0, -vs[2], 0, vs[0], 0, 1, 0, vs[1], -vs[0], 0, 0, 0, 1};   // [-skew(vs) | I]
+        for (int row = 0; row < 3; ++row) {
+          double J[6], r = 0;
+          for (int c = 0; c < 6; ++c) J[c] = W[row * 3] * A[c] + W[row * 3 + 1] * A[6 + c] + W[row * 3 + 2] * A[12 + c];
+          for (int k = 0; k < 3; ++k) r += W[row * 3 + k] * d[k];
+          for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += J[a] * J[b]; JTr[a] += J[a] * r; }
+        }
+      } else {
+        const double *nt = &tgt_nrm[3ll * res.idx[i]];
+        double J[6];
+        cross3(vs, nt, J);
+        J[3] = nt[0]; J[4] = nt[1]; J[5] = nt[2];
+        const double r = dot3(d, nt);
+        for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += J[a] * J[b]; JTr[a] += J[a] * r; }
+      }
+    }
+    double upd[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, x[6], nb[6];
+    for (int k = 0; k < 6; ++k) nb[k] = -JTr[k];
+    if (res.n_corr > 0 && solve6(JTJ, nb, x)) vec6_to_mat4(x, upd);      // failure / no pairs: identity update
+    double Tn[16];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) { double v = 0; for (int k = 0; k < 4; ++k) v += upd[r * 4 + k] * T[k * 4 + c]; Tn[r * 4 + c] = v; }
+    std::memcpy(T, Tn, sizeof(T));
+    oracle_transform(pcd.data(), n_est, upd);
+    if (method == 2) rotate_covs(src_cov, upd);
+    backup = res;
+    icp_evaluate(tree, pcd.data(), n_est, max_dist, res);
+    if (std::fabs(backup.fitness - res.fitness) < rel_fitness && std::fabs(backup.rmse - res.rmse) < rel_rmse) { ++it; break; }
+  }
+  std::memcpy(T_out, T, sizeof(T));
+  *fitness = res.fitness; *inlier_rmse = res.rmse; *n_corr = res.n_corr; *iterations = it;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oracle_estimate_normals_knn(const double *xyz, int64_t n, int knn, double *normals_out) {
+  std::vector<double> nr;
+  estimate_normals_knn(xyz, n, knn, nr);
+  std::memcpy(normals_out, nr.data(), sizeof(double) * 3 * (size_t)n);
+  return 0;
+}
+
+int oracle_gicp_covariance(const double normal[3], double eps, double cov_out[9]) {
+  gicp_covariance(normal, eps, cov_out);
+  return 0;
+}
+
+int oracle_icp_generalized(const double *est, int64_t n_est, const double *gt, int64_t n_gt, double max_dist, int max_iter,
+                           double rel_fitness, double rel_rmse, const double T_init[16], double T_out[16], double *fitness,
+                           double *inlier_rmse, int64_t *n_corr, int32_t *iterations) {
+  return icp_normal_equations(2, est, n_est, gt, n_gt, nullptr, max_dist, max_iter, rel_fitness, rel_rmse, T_init, T_out,
+                              fitness, inlier_rmse, n_corr, iterations);
+}
+
+int oracle_icp_point_to_plane(const double *est, int64_t n_est, const double *gt, int64_t n_gt, const double *gt_normals,
+                              double max_dist, int max_iter, double rel_fitness, double rel_rmse, const double T_init[16],
+                              double T_out[16], double *fitness, double *inlier_rmse, int64_t *n_corr, int32_t *iterations) {
+  return icp_normal_equations(1, est, n_est, gt, n_gt, gt_normals, max_dist, max_iter, rel_fitness, rel_rmse, T_init, T_out,
+                              fitness, inlier_rmse, n_corr, iterations);
 }
 
 }  // extern "C"

@@ -47,6 +47,12 @@ def lib():
         L.oracle_icp_point_to_point.argtypes = [dp, C.c_int64, dp, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double, dp, dp,
                                                 dp, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.oracle_voxel_downsample.argtypes = [dp, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.POINTER(dp)]
+        L.oracle_estimate_normals_knn.argtypes = [dp, C.c_int64, C.c_int, dp]
+        L.oracle_gicp_covariance.argtypes = [dp, C.c_double, dp]
+        L.oracle_icp_generalized.argtypes = [dp, C.c_int64, dp, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double, dp, dp,
+                                             dp, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        L.oracle_icp_point_to_plane.argtypes = [dp, C.c_int64, dp, C.c_int64, dp, C.c_double, C.c_int, C.c_double, C.c_double, dp,
+                                                dp, dp, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 
@@ -180,3 +186,43 @@ def icp_point_to_point(est, gt, max_dist, T_init=None, max_iter=30, rel_fitness=
     lib().oracle_icp_point_to_point(_dptr(e), e.shape[0], _dptr(g), g.shape[0], float(max_dist), int(max_iter), float(rel_fitness),
                                     float(rel_rmse), _dptr(Ti), _dptr(To), C.byref(fit), C.byref(rm), C.byref(nc), C.byref(it))
     return To.reshape(4, 4), fit.value, rm.value, nc.value, it.value
+
+
+def estimate_normals_knn(xyz, knn=20):
+    """open3d PointCloud::EstimateNormals(KDTreeSearchParamKNN(knn)) on a cloud without normals [ext-gicp]."""
+    a = _cloud(xyz)
+    out = np.empty_like(a)
+    lib().oracle_estimate_normals_knn(_dptr(a), a.shape[0], int(knn), _dptr(out))
+    return out
+
+
+def gicp_covariance(normal, eps=1e-3):
+    n = np.ascontiguousarray(normal, dtype=np.float64).reshape(3)
+    out = np.empty(9, np.float64)
+    lib().oracle_gicp_covariance(_dptr(n), float(eps), _dptr(out))
+    return out.reshape(3, 3)
+
+
+def _icp_call(fn, e, g, extra, max_dist, T_init, max_iter, rel_fitness, rel_rmse):
+    Ti = np.ascontiguousarray(np.eye(4) if T_init is None else T_init, dtype=np.float64).reshape(16)
+    To = np.empty(16, np.float64)
+    fit, rm = C.c_double(0), C.c_double(0)
+    nc, it = C.c_int64(0), C.c_int32(0)
+    rc = fn(_dptr(e), e.shape[0], _dptr(g), g.shape[0], *extra, float(max_dist), int(max_iter), float(rel_fitness),
+            float(rel_rmse), _dptr(Ti), _dptr(To), C.byref(fit), C.byref(rm), C.byref(nc), C.byref(it))
+    if rc != 0:
+        raise RuntimeError(f"oracle ICP failed: {rc}")
+    return To.reshape(4, 4), fit.value, rm.value, nc.value, it.value
+
+
+def icp_generalized(est, gt, max_dist, T_init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """open3d RegistrationGeneralizedICP + TransformationEstimationForGeneralizedICP() (map_eval.cpp:1381-1385).
+    Returns (T 4x4, fitness, inlier_rmse, n_corr, iterations)."""
+    return _icp_call(lib().oracle_icp_generalized, _cloud(est), _cloud(gt), (), max_dist, T_init, max_iter, rel_fitness, rel_rmse)
+
+
+def icp_point_to_plane(est, gt, gt_normals, max_dist, T_init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """open3d RegistrationICP + TransformationEstimationPointToPlane (map_eval.cpp:1375-1379); the target needs normals."""
+    nr = _cloud(gt_normals)
+    return _icp_call(lib().oracle_icp_point_to_plane, _cloud(est), _cloud(gt), (_dptr(nr),), max_dist, T_init, max_iter,
+                     rel_fitness, rel_rmse)

@@ -1,6 +1,9 @@
-"""Full-size (BASELINE.json C3: 10 M vs 10 M points) checks through size-independent properties — the CPU oracle cannot
-run these sizes in test time, so the CUDA path is checked against itself under transformations that must not change the
-answer, and against brute force on a random sample of queries."""
+"""Full-size (BASELINE.json C3: 10 M vs 10 M points) checks: (1) against the CPU oracle's results on the same 10 M vs
+10 M pair, computed once on the B200 box's host cores and committed as tests/golden/c3_oracle.json
+(tests/golden/make_c3_oracle.py); (2) through size-independent properties — the CUDA path against itself under
+transformations that must not change the answer, and against brute force on a random sample of queries."""
+import json
+import os
 import numpy as np
 import pytest
 
@@ -93,3 +96,49 @@ def test_c3_full_size_properties(api, c3):
         j = int(np.argmin(d2))
         assert d20[i] == d2[j] and (idx0[i] == j or d2[idx0[i]] == d2[j])
     # ... and of MME neighbour counts through the validity flags of far-from-typical points is covered at small size
+
+
+def _index_checksum(idx):
+    i = np.arange(idx.shape[0], dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int(np.sum((idx.astype(np.int64) + 1).astype(np.uint64) * (i * np.uint64(2654435761) + np.uint64(1)),
+                          dtype=np.uint64))
+
+
+def test_c3_full_size_against_the_oracle_fixture(api, c3, golden_dir):
+    """Every scalar and integer count of the headline pass against the oracle's run on the same 10 M vs 10 M pair
+    (path A as written + full CD, exactly what bench.py times; its `check` block is the same set of numbers)."""
+    path = os.path.join(golden_dir, "c3_oracle.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/c3_oracle.json not generated yet (tests/golden/make_c3_oracle.py)")
+    ref = json.load(open(path))
+    est, gt, cfg = c3
+    assert ref["n_est"] == len(est) and ref["n_gt"] == len(gt) and ref["tau"] == cfg["tau"]
+    p = A.make_nn_params(cfg["tau"], 1.0)
+    with api.MapEvalB200(vmd_voxel_size=cfg["vmd_voxel_size"]) as ctx:
+        ctx.set_cloud(A.ME_CLOUD_EST, est)
+        ctx.set_cloud(A.ME_CLOUD_GT, gt)
+        mme, ent = ctx.computeMME(A.ME_CLOUD_EST, cfg["nn_radius"], 10, want_entropies=True)
+        nn = ctx.calculateMetricsWithInitialMatrix(p)
+        idx_e, _ = ctx.get_nn(A.ME_CLOUD_EST)
+        idx_g, _ = ctx.get_nn(A.ME_CLOUD_GT)
+        awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5)
+    got = A.struct_to_dict(nn)
+    for d in ("est_to_gt", "gt_to_est"):
+        for k in ("n_source", "n_corr", "n_inlier", "n_ub"):
+            assert got[d][k] == ref["nn"][d][k], (d, k)
+        for k in ("mean", "rmse", "fitness", "sigma", "sum_nn_dist"):
+            np.testing.assert_allclose(got[d][k], ref["nn"][d][k], rtol=1e-9, atol=1e-300, err_msg=f"{d}.{k}")
+    for k in ("cd", "f1", "iou", "full_cd"):
+        np.testing.assert_allclose(got[k], ref["nn"][k], rtol=1e-9, err_msg=k)
+    assert _index_checksum(idx_e) == ref["nn_index_checksum"]["est_to_gt"]
+    assert _index_checksum(idx_g) == ref["nn_index_checksum"]["gt_to_est"]
+    assert mme.n_valid == ref["mme"]["n_valid"] and int(np.count_nonzero(ent)) == ref["mme_nonzero"]
+    np.testing.assert_allclose(mme.mme, ref["mme"]["mme"], rtol=1e-7)
+    np.testing.assert_allclose([mme.min_abs_entropy, mme.max_abs_entropy],
+                               [ref["mme"]["min_abs_entropy"], ref["mme"]["max_abs_entropy"]], rtol=1e-6)
+    np.testing.assert_allclose([ent.sum(), np.abs(ent).sum()], [ref["mme_entropy_sum"], ref["mme_entropy_abs_sum"]], rtol=1e-7)
+    ga = A.struct_to_dict(awd)
+    for k in ("n_pairs", "n_scs", "n_voxels_est", "n_voxels_gt", "n_active", "n_old", "n_new"):
+        assert ga[k] == ref["awd"][k], k
+    np.testing.assert_allclose([ga["awd"], ga["scs"]], [ref["awd"]["awd"], ref["awd"]["scs"]], rtol=1e-8)
