@@ -20,6 +20,10 @@ ME_CUTOFF_DIST_LT_R = 1
 ME_PAIRING_AS_WRITTEN = 0
 ME_PAIRING_GEOMETRIC = 1
 
+ME_ICP_POINT_TO_POINT = 0
+ME_ICP_POINT_TO_PLANE = 1
+ME_ICP_GENERALIZED = 2
+
 ME_N_STAGE_TIMES = 9
 STAGE_NAMES = ("grid_est", "grid_gt", "nn_est_to_gt", "nn_gt_to_est", "mme_est", "mme_gt",
                "voxel_moments", "awd", "scs")

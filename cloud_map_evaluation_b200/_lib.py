@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libmapeval_b200.so")
 # every symbol include/mapeval_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "me_abi_version", "me_create", "me_destroy", "me_last_error", "me_set_stream", "me_set_shard", "me_synchronize",
-    "me_set_cloud", "me_set_cloud_device", "me_transform", "me_voxel_downsample", "me_get_cloud", "me_icp_point_to_point", "me_build_grid", "me_eval_nn_accum", "me_nn_finalize",
+    "me_set_cloud", "me_set_cloud_device", "me_transform", "me_voxel_downsample", "me_get_cloud", "me_icp_point_to_point", "me_icp",
+    "me_set_normals", "me_estimate_normals", "me_get_normals", "me_build_grid", "me_eval_nn_accum", "me_nn_finalize",
     "me_eval_nn", "me_get_nn", "me_eval_mme_accum", "me_mme_finalize", "me_eval_mme", "me_get_entropies",
     "me_eval_awd", "me_awd_from_rows", "me_free", "me_get_stage_times", "me_launch_count",
 )
@@ -51,6 +52,10 @@ def load():
     L.me_transform.argtypes = [ctx, C.c_int, dp]
     L.me_awd_from_rows.argtypes = [ctx, dp, C.c_int64, C.c_double, C.c_int32, dp, C.POINTER(A.me_awd_result)]
     L.me_icp_point_to_point.argtypes = [ctx, C.c_double, C.c_int32, C.c_double, C.c_double, dp, C.POINTER(A.me_icp_result)]
+    L.me_icp.argtypes = [ctx, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, dp, C.POINTER(A.me_icp_result)]
+    L.me_set_normals.argtypes = [ctx, C.c_int, dp, C.c_int64]
+    L.me_estimate_normals.argtypes = [ctx, C.c_int, C.c_int32]
+    L.me_get_normals.argtypes = [ctx, C.c_int, dp]
     L.me_voxel_downsample.argtypes = [ctx, C.c_int, C.c_double, C.POINTER(C.c_int64)]
     L.me_get_cloud.argtypes = [ctx, C.c_int, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.me_build_grid.argtypes = [ctx, C.c_int]

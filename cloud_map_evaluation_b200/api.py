@@ -100,16 +100,28 @@ class MapEvalB200:
         self._check(self._L.me_transform(self._ctx, which, T.ctypes.data_as(C.POINTER(C.c_double))))
 
     def performICPRegistration(self, max_correspondence_distance, T_init=None, max_iteration=30, relative_fitness=1e-6,
-                               relative_rmse=1e-6):
-        """map_eval.cpp:1366-1394 case 0: RegistrationICP + TransformationEstimationPointToPoint; the estimated cloud held
-        by the context is transformed by the result.  Returns (T 4x4, me_icp_result)."""
+                               relative_rmse=1e-6, method=A.ME_ICP_POINT_TO_POINT):
+        """map_eval.cpp:1366-1394: RegistrationICP with the point-to-point (method 0) or point-to-plane (1) estimation, or
+        RegistrationGeneralizedICP (2, `registration_methods` of the config); the estimated cloud held by the context is
+        transformed by the result.  Returns (T 4x4, me_icp_result)."""
         T = np.ascontiguousarray(np.eye(4) if T_init is None else T_init, dtype=np.float64).reshape(16)
         out = A.me_icp_result()
-        self._check(self._L.me_icp_point_to_point(self._ctx, float(max_correspondence_distance), int(max_iteration),
-                                                  float(relative_fitness), float(relative_rmse),
-                                                  T.ctypes.data_as(C.POINTER(C.c_double)), C.byref(out)))
+        self._check(self._L.me_icp(self._ctx, int(method), float(max_correspondence_distance), int(max_iteration),
+                                   float(relative_fitness), float(relative_rmse),
+                                   T.ctypes.data_as(C.POINTER(C.c_double)), C.byref(out)))
         self._keep[A.ME_CLOUD_EST] = None
         return np.array(list(out.transformation)).reshape(4, 4), out
+
+    def set_normals(self, which, normals):
+        a = np.ascontiguousarray(normals, dtype=np.float64)
+        self._check(self._L.me_set_normals(self._ctx, which, a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0]))
+
+    def estimate_normals(self, which, knn=20):
+        """PointCloud::EstimateNormals(KDTreeSearchParamKNN(knn)); returns the (N, 3) normals in caller order."""
+        self._check(self._L.me_estimate_normals(self._ctx, which, int(knn)))
+        out = np.empty((self.n[which], 3), np.float64)
+        self._check(self._L.me_get_normals(self._ctx, which, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def voxel_downsample(self, which, voxel_size):
         """PointCloud::VoxelDownSample on the held cloud (map_eval.cpp:38-39); returns the new point count."""

@@ -45,8 +45,12 @@ int ensure_work(me_ctx *ctx, size_t bytes) {
   return ME_OK;
 }
 
-static void invalidate(Cloud &c) {
+void invalidate_cloud(Cloud &c) {
   c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false; c.entropy_caller_valid = false;
+}
+static void invalidate(Cloud &c) {      // a new cloud: its normals go as well
+  invalidate_cloud(c);
+  c.normal_valid = false;
 }
 
 static void free_cloud(Cloud &c) {
@@ -60,6 +64,7 @@ static void free_cloud(Cloud &c) {
   if (c.d_nn_sq) cudaFree(c.d_nn_sq);
   if (c.d_entropy) cudaFree(c.d_entropy);
   if (c.d_entropy_caller) cudaFree(c.d_entropy_caller);
+  if (c.d_normal) cudaFree(c.d_normal);
   if (c.d_tiles) cudaFree(c.d_tiles);
   if (c.d_tile_pos) cudaFree(c.d_tile_pos);
   if (c.upload_done) cudaEventDestroy(c.upload_done);
@@ -246,7 +251,42 @@ int me_icp_point_to_point(me_ctx *ctx, double max_correspondence_distance, int32
                           double relative_rmse, const double T_init[16], me_icp_result *out) {
   ME_ENTER(ctx);
   if (!T_init || !out) return fail(ctx, ME_ERR_INVALID, "null argument");
-  return run_icp(ctx, max_correspondence_distance, max_iteration, relative_fitness, relative_rmse, T_init, out);
+  return run_icp(ctx, ME_ICP_POINT_TO_POINT, max_correspondence_distance, max_iteration, relative_fitness, relative_rmse, T_init, out);
+}
+
+int me_icp(me_ctx *ctx, int32_t method, double max_correspondence_distance, int32_t max_iteration, double relative_fitness,
+           double relative_rmse, const double T_init[16], me_icp_result *out) {
+  ME_ENTER(ctx);
+  if (!T_init || !out) return fail(ctx, ME_ERR_INVALID, "null argument");
+  return run_icp(ctx, method, max_correspondence_distance, max_iteration, relative_fitness, relative_rmse, T_init, out);
+}
+
+int me_set_normals(me_ctx *ctx, int which, const double *normals_host, int64_t n) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad cloud id");
+  Cloud &c = ctx->cloud[which];
+  if (!normals_host || n != c.n || n <= 0) return fail(ctx, ME_ERR_INVALID, "me_set_normals: one normal per point of the cloud held by the context");
+  ME_TRY(ensure(ctx, (void **)&c.d_normal, &c.cap_normal, 3 * c.n, sizeof(double)));
+  ME_CUDA(ctx, cudaMemcpyAsync(c.d_normal, normals_host, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  c.normal_valid = true;
+  return ME_OK;
+}
+
+int me_estimate_normals(me_ctx *ctx, int which, int32_t knn) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad cloud id");
+  return estimate_normals(ctx, which, knn, 0);
+}
+
+int me_get_normals(me_ctx *ctx, int which, double *normals_host) {
+  ME_ENTER(ctx);
+  if ((which != ME_CLOUD_EST && which != ME_CLOUD_GT) || !normals_host) return fail(ctx, ME_ERR_INVALID, "bad arguments");
+  Cloud &c = ctx->cloud[which];
+  if (!c.normal_valid) return fail(ctx, ME_ERR_INVALID, "me_get_normals: the cloud has no normals");
+  ME_CUDA(ctx, cudaMemcpyAsync(normals_host, c.d_normal, (size_t)c.n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ME_OK;
 }
 
 int me_build_grid(me_ctx *ctx, int which) {

@@ -559,6 +559,15 @@ __global__ void __launch_bounds__(kThreads) transform_kernel(double *__restrict_
   }
 }
 
+// PointCloud::TransformNormals: n' = T.block<3,3>(0,0) n
+__global__ void __launch_bounds__(kThreads) rotate_normals_kernel(double *__restrict__ nrm, long long n, Mat16 T) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double x = nrm[3 * i], y = nrm[3 * i + 1], z = nrm[3 * i + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) nrm[3 * i + r] = T.t[r * 4] * x + T.t[r * 4 + 1] * y + T.t[r * 4 + 2] * z;
+  }
+}
+
 int transform_cloud(me_ctx *ctx, int which, const double T[16]) {
   Cloud &c = ctx->cloud[which];
   if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
@@ -569,7 +578,11 @@ int transform_cloud(me_ctx *ctx, int which, const double T[16]) {
   int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
   transform_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, M);
   ME_LAUNCH_CHECK(ctx);
-  c.grid_valid = false; c.bbox_valid = false; c.nn_valid = false; c.entropy_valid = false; c.entropy_caller_valid = false;
+  if (c.normal_valid) {      // Open3D's PointCloud::Transform moves the normals along
+    rotate_normals_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_normal, c.n, M);
+    ME_LAUNCH_CHECK(ctx);
+  }
+  invalidate_cloud(c);
   return ME_OK;
 }
 

@@ -4,7 +4,8 @@
 // ReadPointCloudOption("auto", remove_nan = true, remove_infinite = true, print_progress = true), map_eval.cpp:6-21),
 // which is not available here.  Only the x/y/z fields are consumed by the metric path; points with a non-finite
 // coordinate are dropped, as that option does.  Coordinates are widened to double — the type of Open3D's
-// PointCloud::points_.
+// PointCloud::points_.  Normals (PCD normal_x / normal_y / normal_z, PLY nx / ny / nz) are read on request: point-to-plane ICP
+// (registration_methods: 1) needs them on the ground-truth cloud, as Open3D's PointCloud::normals_.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -53,12 +54,14 @@ inline bool lzf_decompress(const unsigned char *in, size_t in_len, unsigned char
   return op == out_len;
 }
 
-inline void push_if_finite(std::vector<double> &xyz, double x, double y, double z) {
-  if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) { xyz.push_back(x); xyz.push_back(y); xyz.push_back(z); }
+inline bool push_if_finite(std::vector<double> &xyz, double x, double y, double z) {
+  if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) { xyz.push_back(x); xyz.push_back(y); xyz.push_back(z); return true; }
+  return false;
 }
 
 // returns false if the file cannot be opened / parsed; xyz = N x 3 AoS
-inline bool read_pcd(const std::string &path, std::vector<double> &xyz, std::string *err = nullptr) {
+// normals (nullable): filled with N x 3 normals when the file carries them, left empty otherwise
+inline bool read_pcd(const std::string &path, std::vector<double> &xyz, std::string *err = nullptr, std::vector<double> *normals = nullptr) {
   std::ifstream in(path, std::ios::binary);
   if (!in.is_open()) { if (err) *err = "cannot open " + path; return false; }
   std::vector<Field> fields;
@@ -80,14 +83,19 @@ inline bool read_pcd(const std::string &path, std::vector<double> &xyz, std::str
     else if (tag == "DATA") { ls >> data_kind; break; }
   }
   if (points < 0) points = width * height;
-  int step = 0, ix = -1, iy = -1, iz = -1;
+  int step = 0, ix = -1, iy = -1, iz = -1, nx = -1, ny = -1, nz = -1;
   for (size_t i = 0; i < fields.size(); ++i) {
     fields[i].offset = step;
     step += fields[i].size * fields[i].count;
     if (fields[i].name == "x") ix = (int)i;
     if (fields[i].name == "y") iy = (int)i;
     if (fields[i].name == "z") iz = (int)i;
+    if (fields[i].name == "normal_x") nx = (int)i;
+    if (fields[i].name == "normal_y") ny = (int)i;
+    if (fields[i].name == "normal_z") nz = (int)i;
   }
+  const bool want_n = normals && nx >= 0 && ny >= 0 && nz >= 0;
+  if (normals) normals->clear();
   if (ix < 0 || iy < 0 || iz < 0 || data_kind.empty()) { if (err) *err = "PCD header without x/y/z fields or DATA line: " + path; return false; }
   xyz.clear();
   xyz.reserve((size_t)points * 3);
@@ -101,7 +109,9 @@ inline bool read_pcd(const std::string &path, std::vector<double> &xyz, std::str
       if (vals.empty()) continue;
       // field index -> value index (COUNT may exceed 1 for non-xyz fields)
       auto value_of = [&](int f) { int k = 0; for (int i = 0; i < f; ++i) k += fields[i].count; return k < (int)vals.size() ? vals[k] : std::nan(""); };
-      push_if_finite(xyz, value_of(ix), value_of(iy), value_of(iz));
+      if (push_if_finite(xyz, value_of(ix), value_of(iy), value_of(iz)) && want_n) {
+        normals->push_back(value_of(nx)); normals->push_back(value_of(ny)); normals->push_back(value_of(nz));
+      }
     }
   } else if (data_kind == "binary") {
     std::vector<unsigned char> buf((size_t)points * step);
@@ -109,9 +119,8 @@ inline bool read_pcd(const std::string &path, std::vector<double> &xyz, std::str
     if ((size_t)in.gcount() != buf.size()) { if (err) *err = "truncated binary PCD: " + path; return false; }
     for (long long i = 0; i < points; ++i) {
       const unsigned char *p = buf.data() + (size_t)i * step;
-      push_if_finite(xyz, read_scalar(p + fields[ix].offset, fields[ix].size, fields[ix].type),
-                     read_scalar(p + fields[iy].offset, fields[iy].size, fields[iy].type),
-                     read_scalar(p + fields[iz].offset, fields[iz].size, fields[iz].type));
+      auto at = [&](int f) { return read_scalar(p + fields[f].offset, fields[f].size, fields[f].type); };
+      if (push_if_finite(xyz, at(ix), at(iy), at(iz)) && want_n) { normals->push_back(at(nx)); normals->push_back(at(ny)); normals->push_back(at(nz)); }
     }
   } else if (data_kind == "binary_compressed") {
     uint32_t comp = 0, uncomp = 0;
@@ -129,7 +138,7 @@ inline bool read_pcd(const std::string &path, std::vector<double> &xyz, std::str
     for (size_t f = 0; f < fields.size(); ++f) { base[f] = off; off += (size_t)fields[f].size * fields[f].count * points; }
     for (long long i = 0; i < points; ++i) {
       auto at = [&](int f) { return read_scalar(buf.data() + base[f] + (size_t)i * fields[f].size * fields[f].count, fields[f].size, fields[f].type); };
-      push_if_finite(xyz, at(ix), at(iy), at(iz));
+      if (push_if_finite(xyz, at(ix), at(iy), at(iz)) && want_n) { normals->push_back(at(nx)); normals->push_back(at(ny)); normals->push_back(at(nz)); }
     }
   } else {
     if (err) *err = "unsupported PCD DATA kind '" + data_kind + "': " + path;
@@ -138,7 +147,7 @@ inline bool read_pcd(const std::string &path, std::vector<double> &xyz, std::str
   return true;
 }
 
-inline bool read_ply(const std::string &path, std::vector<double> &xyz, std::string *err = nullptr) {
+inline bool read_ply(const std::string &path, std::vector<double> &xyz, std::string *err = nullptr, std::vector<double> *normals = nullptr) {
   std::ifstream in(path, std::ios::binary);
   if (!in.is_open()) { if (err) *err = "cannot open " + path; return false; }
   std::string line, format;
@@ -175,13 +184,18 @@ inline bool read_ply(const std::string &path, std::vector<double> &xyz, std::str
     return 4;
   };
   auto kind_of = [](const std::string &t) { return (t == "float" || t == "double" || t == "float32" || t == "float64") ? 'F' : (t[0] == 'u' ? 'U' : 'I'); };
-  int step = 0, ox = -1, oy = -1, oz = -1, px = -1, py = -1, pz = -1;
+  int step = 0, ox = -1, oy = -1, oz = -1, px = -1, py = -1, pz = -1, on[3] = {-1, -1, -1}, pn[3] = {-1, -1, -1};
   for (size_t i = 0; i < props.size(); ++i) {
     if (props[i].name == "x") { ox = step; px = (int)i; }
     if (props[i].name == "y") { oy = step; py = (int)i; }
     if (props[i].name == "z") { oz = step; pz = (int)i; }
+    if (props[i].name == "nx") { on[0] = step; pn[0] = (int)i; }
+    if (props[i].name == "ny") { on[1] = step; pn[1] = (int)i; }
+    if (props[i].name == "nz") { on[2] = step; pn[2] = (int)i; }
     step += size_of(props[i].type);
   }
+  const bool want_n = normals && pn[0] >= 0 && pn[1] >= 0 && pn[2] >= 0;
+  if (normals) normals->clear();
   if (px < 0 || py < 0 || pz < 0) { if (err) *err = "PLY vertex element without x/y/z: " + path; return false; }
   xyz.clear();
   xyz.reserve((size_t)nvert * 3);
@@ -193,7 +207,7 @@ inline bool read_ply(const std::string &path, std::vector<double> &xyz, std::str
       for (size_t k = 0; k < props.size() && (ls >> tok); ++k) {   // stod understands nan / inf, operator>> does not
         try { v[k] = std::stod(tok); } catch (...) { v[k] = std::nan(""); }
       }
-      push_if_finite(xyz, v[px], v[py], v[pz]);
+      if (push_if_finite(xyz, v[px], v[py], v[pz]) && want_n) for (int a = 0; a < 3; ++a) normals->push_back(v[pn[a]]);
     }
   } else if (format == "binary_little_endian") {
     std::vector<unsigned char> buf((size_t)nvert * step);
@@ -201,9 +215,10 @@ inline bool read_ply(const std::string &path, std::vector<double> &xyz, std::str
     if ((size_t)in.gcount() != buf.size()) { if (err) *err = "truncated binary PLY: " + path; return false; }
     for (long long i = 0; i < nvert; ++i) {
       const unsigned char *p = buf.data() + (size_t)i * step;
-      push_if_finite(xyz, read_scalar(p + ox, size_of(props[px].type), kind_of(props[px].type)),
-                     read_scalar(p + oy, size_of(props[py].type), kind_of(props[py].type)),
-                     read_scalar(p + oz, size_of(props[pz].type), kind_of(props[pz].type)));
+      if (push_if_finite(xyz, read_scalar(p + ox, size_of(props[px].type), kind_of(props[px].type)),
+                         read_scalar(p + oy, size_of(props[py].type), kind_of(props[py].type)),
+                         read_scalar(p + oz, size_of(props[pz].type), kind_of(props[pz].type))) && want_n)
+        for (int a = 0; a < 3; ++a) normals->push_back(read_scalar(p + on[a], size_of(props[pn[a]].type), kind_of(props[pn[a]].type)));
     }
   } else {
     if (err) *err = "unsupported PLY format '" + format + "': " + path;

@@ -13,8 +13,13 @@
 //   calculateVMD                          :240-390        calculateVMD          -> me_eval_awd (+ the two text files)
 //   saveMmeResults / saveRegistrationResults :392-482     same line formats in map_results.txt
 //
-// Not built (out of the hot-path scope): VoxelDownSample (N1), ICP / GICP (N2), rendered PCDs (N3).
-// process() says so and returns -1 where the reference would need them.
+//   VoxelDownSample                  map_eval.cpp:38-39    me_voxel_downsample (§8f N1)
+//   performRegistration / performICPRegistration :191-237, 1366-1394   performRegistration -> me_icp (§8f N2: point-to-point,
+//                                                         point-to-plane and generalized ICP) + calculateMetrics(reg)
+//   rendered clouds                  :485-499, 568-736    render.hpp (§8f N3): entropy maps, raw / inlier NN-distance maps
+// Limits of this driver: point-to-plane ICP (registration_methods: 1) needs normals in the ground-truth FILE, as in the
+// reference (Open3D raises without them), and no down-sampling (VoxelDownSample's normal averaging is not built);
+// validate() rejects such a configuration before anything is written.
 #pragma once
 #include <algorithm>
 #include <chrono>
@@ -178,6 +183,23 @@ class TicToc {   // include/tic_toc.h:10-25 (milliseconds, system_clock)
 
 class MapEvalB200 {
  public:
+  // Configurations this driver cannot run, reported BEFORE map_results.txt is opened (no partial record is left behind).
+  static bool validate(const Param &p, std::string *why) {
+    if (p.evaluate_using_initial_) return true;
+    if (p.evaluation_method_ < 0 || p.evaluation_method_ > 2) {
+      *why = "Invalid registration type specified (registration_methods: " + std::to_string(p.evaluation_method_) +
+             "; 0 = point-to-point, 1 = point-to-plane, 2 = generalized ICP, map_eval.cpp:1368-1390)";
+      return false;
+    }
+    if (p.evaluation_method_ == 1 && p.downsample_size > 0) {
+      *why = "registration_methods: 1 (point-to-plane ICP) takes the target normals from the ground-truth file; with "
+             "downsample_size > 0 they would have to be averaged per voxel (Open3D VoxelDownSample), which this driver does "
+             "not do: set downsample_size: 0, or use registration_methods: 0 / 2";
+      return false;
+    }
+    return true;
+  }
+
   explicit MapEvalB200(Param &param) : param_(param) {   // map_eval.h:123-189
     t1 = t2 = t3 = t4 = t5 = t6 = t7 = 0.0;
     if (param_.pcd_file_name_ == "merged_maps_all_trans.pcd") subfolder = "merged_maps_all_results/";
@@ -211,9 +233,9 @@ class MapEvalB200 {
   int process();                                   // map_eval.cpp:4-102
   int computeMME();                                // map_eval.cpp:149-189
   int calculateMetricsWithInitialMatrix();         // map_eval.cpp:1204-1260
-  int performRegistration();                       // map_eval.cpp:191-237, 1366-1394 (point-to-point ICP only), 1147-1202
+  int performRegistration();                       // map_eval.cpp:191-237, 1366-1394 (all three registration methods), 1147-1202
   int calculateVMD();                              // map_eval.cpp:240-390
-  void saveMmeResults();                           // map_eval.cpp:392-421 (text line only)
+  void saveMmeResults();                           // map_eval.cpp:392-421 (result line + the rendered entropy clouds)
   void saveRegistrationResults();                  // map_eval.cpp:424-482 (text lines only)
 
   Param param_;
@@ -236,6 +258,7 @@ class MapEvalB200 {
   GpuGroup gpus_;            // one context per GPU; rank r evaluates the r-th shard of every sweep's query range
   me_ctx *ctx_ = nullptr;    // = gpus_.ctx(0): the voxel stage and the single-GPU calls
   std::vector<double> map_3d_, gt_3d_;   // N x 3 fp64, the layout of open3d PointCloud::points_ (as loaded)
+  std::vector<double> gt_normals_;       // PointCloud::normals_ of the ground truth (point-to-plane ICP only)
   int64_t n_est_ = 0, n_gt_ = 0;         // point counts after VoxelDownSample (the clouds the metrics see)
   double t1, t2, t3, t4, t5, t6, t7, t_fcd = 0.0, t_acc = 0.0;
   double t_vmd = 0.0, t_v = 0.0, t_cdf = 0.0, t_scs = 0.0;
@@ -246,10 +269,16 @@ class MapEvalB200 {
 inline int MapEvalB200::process() {
   TicToc tic_toc;
   std::string err;
+  if (!validate(param_, &err)) {
+    std::cerr << "ERROR: " << err << std::endl;
+    return -1;
+  }
+  // point-to-plane ICP: Open3D needs normals on the target cloud; they can only come from the ground-truth file
+  std::vector<double> *want_normals = (!param_.evaluate_using_initial_ && param_.evaluation_method_ == 1) ? &gt_normals_ : nullptr;
   std::string file_extension = param_.map_gt_path_.substr(param_.map_gt_path_.find_last_of(".") + 1);
   bool gt_ok = false;
-  if (file_extension == "pcd") gt_ok = cloud_io::read_pcd(param_.map_gt_path_, gt_3d_, &err);
-  else if (file_extension == "ply") gt_ok = cloud_io::read_ply(param_.map_gt_path_, gt_3d_, &err);
+  if (file_extension == "pcd") gt_ok = cloud_io::read_pcd(param_.map_gt_path_, gt_3d_, &err, want_normals);
+  else if (file_extension == "ply") gt_ok = cloud_io::read_ply(param_.map_gt_path_, gt_3d_, &err, want_normals);
   else {
     std::cerr << "ERROR: Unsupported ground truth file format: " << param_.map_gt_path_ << std::endl;
     return -1;
@@ -264,6 +293,11 @@ inline int MapEvalB200::process() {
   }
   if (map_3d_.empty() || gt_3d_.empty()) {
     std::cerr << "ERROR: One or both point clouds are empty!" << std::endl;
+    return -1;
+  }
+  if (want_normals && gt_normals_.size() != gt_3d_.size()) {
+    std::cerr << "ERROR: TransformationEstimationPointToPlane requires pre-computed normal vectors for the target PointCloud: "
+              << param_.map_gt_path_ << " carries none (registration_methods: 1)." << std::endl;
     return -1;
   }
   if (!gpus_.create(std::max(1, param_.n_gpus_), param_.gpu_device_, param_.vmd_voxel_size_)) return fail("cannot create the B200 context(s)");
@@ -432,6 +466,11 @@ inline int MapEvalB200::calculateMetricsWithInitialMatrix() {
   if (!gpus_.reduce_nn(e2g, g2e)) return fail("all-reduce of the NN accumulators");
   if (me_nn_finalize(&p, &e2g[0], &g2e[0], n_est_, n_gt_, &nn_) != ME_OK) return fail("me_nn_finalize");
   t_acc = tic.toc() / 1000.0;
+  if (nn_.gt_to_est.n_ub > 0)
+    std::cerr << "WARNING: " << nn_.gt_to_est.n_ub << " gt->est pairs index past the end of a cloud (the reference reads out of "
+                 "bounds there, map_eval.cpp:1233 vs :1093-1094: undefined behaviour); they are left out of the gt->est statistics, "
+                 "so the CD vector / gt->est lines are not comparable with a reference run.  geometric_gt_pairing: true pairs "
+                 "the points geometrically instead." << std::endl;
   if (param_.save_immediate_result_ && renderDistances(false) != 0) return -1;
   std::cout << "INFO: Chamfer Distance: " << eigenRow(nn_.cd, 5, 6) << std::endl;
   std::cout << "INFO: F1 Score: " << eigenRow(nn_.f1, 5, 6) << std::endl;
@@ -443,20 +482,17 @@ inline int MapEvalB200::calculateMetricsWithInitialMatrix() {
 
 inline int MapEvalB200::performRegistration() {
   TicToc tic_toc;
-  if (param_.evaluation_method_ != 0) {
-    std::cerr << "ERROR: registration_methods: " << param_.evaluation_method_ << " ("
-              << (param_.evaluation_method_ == 1 ? "point-to-plane ICP" : param_.evaluation_method_ == 2 ? "generalized ICP" : "invalid")
-              << ") is not part of the B200 path (SURVEY.md §8f N2): use registration_methods: 0 (point-to-point ICP), or align "
-                 "the clouds first (initial_matrix) and set evaluate_using_initial: true." << std::endl;
-    return -1;
-  }
   if (gpus_.size() > 1) std::cout << "INFO: ICP runs on GPU " << param_.gpu_device_ << " only; the metric sweeps are sharded." << std::endl;
   // ICP needs all correspondences on one GPU: run it on a single-shard context, then hand every GPU the aligned cloud
   me_icp_result reg{};
   me_set_shard(ctx_, 0, 1);
-  const int rc = me_icp_point_to_point(ctx_, param_.icp_max_distance_, 30, 1e-6, 1e-6, param_.initial_matrix_, &reg);
+  int rc = ME_OK;
+  if (param_.evaluation_method_ == ME_ICP_POINT_TO_PLANE)
+    rc = me_set_normals(ctx_, ME_CLOUD_GT, gt_normals_.data(), (int64_t)(gt_normals_.size() / 3));
+  // performICPRegistration (:1366-1394): ICPConvergenceCriteria() = {1e-6, 1e-6, 30}
+  if (rc == ME_OK) rc = me_icp(ctx_, param_.evaluation_method_, param_.icp_max_distance_, 30, 1e-6, 1e-6, param_.initial_matrix_, &reg);
   me_set_shard(ctx_, 0, gpus_.size());
-  if (rc != ME_OK) return fail("me_icp_point_to_point");
+  if (rc != ME_OK) return fail("me_icp");
   t4 = tic_toc.toc();
   std::cout << "INFO: ICP registration time: " << (t4 - t3) / 1000.0 << " [s]" << std::endl;
   std::cout << "INFO: Aligned transformation: \n" << eigenMatrix4(reg.transformation, 6) << std::endl;

@@ -60,6 +60,13 @@ int main(int argc, char **argv) {
     dumpParam(param, std::cout);
     return EXIT_SUCCESS;
   }
+  {
+    std::string why;
+    if (!MapEvalB200::validate(param, &why)) {      // before the constructor opens map_results.txt
+      std::cerr << "\n[ERROR] " << why << "\n";
+      return EXIT_FAILURE;
+    }
+  }
   displayProgramInformation(param);
   std::cout << "Starting evaluation...\n================================================================================\n\n";
   MapEvalB200 map_eval(param);

@@ -72,7 +72,7 @@ typedef struct {
   int32_t device;          /* CUDA device ordinal                                          */
   int32_t rank, world;     /* this context evaluates queries [rank*N/world,(rank+1)*N/world) */
   void   *stream;          /* cudaStream_t to launch on; NULL = library-owned stream       */
-  double  nn_cell_size;    /* edge of the hashed-grid cells in metres; <= 0 = auto         */
+  double  nn_cell_size;    /* edge of the lattice cells in metres; <= 0 = auto         */
   int64_t max_grid_cells;  /* budget for the dense cell table; <= 0 = automatic (2^28 .. 2^31 with the cloud sizes) */
   double  vmd_voxel_size;  /* voxel edge the lattices should align to (the config's vmd_voxel_size);
                               <= 0 = unknown: me_eval_awd then re-lays the clouds out once     */
@@ -142,7 +142,10 @@ typedef struct {
   int64_t n_active, n_old, n_new;    /* voxel_calculator.cpp:170 */
 } me_awd_result;
 
-/* ---- N2: point-to-point ICP (registration_methods: 0) -------------------------------------------------- */
+/* ---- N2: registration (registration_methods: 0 point-to-point, 1 point-to-plane, 2 generalized ICP) --------- */
+#define ME_ICP_POINT_TO_POINT 0     /* map_eval.cpp:1370-1374 */
+#define ME_ICP_POINT_TO_PLANE 1     /* :1375-1379 */
+#define ME_ICP_GENERALIZED    2     /* :1380-1385, the value every shipped config uses */
 
 typedef struct {             /* == open3d RegistrationResult (map_eval.cpp:1367-1394) */
   double  transformation[16];        /* row-major 4x4: registration_result.transformation_ -> trans            */
@@ -181,10 +184,23 @@ ME_API int  me_get_cloud(me_ctx *ctx, int which, double *xyz_host, int64_t capac
  * icp_max_distance, initial_matrix, TransformationEstimationPointToPoint(), ICPConvergenceCriteria{relative_fitness,
  * relative_rmse, max_iteration} = {1e-6, 1e-6, 30}).  On return the estimated cloud held by the context is the original
  * cloud transformed once by the result (map_3d_->Transform(trans), :1392), ready for me_eval_nn with
- * ME_CUTOFF_DIST_LT_R / ME_PAIRING_GEOMETRIC / want_full_cd (calculateMetrics, :1147-1202).  world must be 1.
- * Point-to-plane (case 1) and generalized ICP (case 2) are not provided. */
+ * ME_CUTOFF_DIST_LT_R / ME_PAIRING_GEOMETRIC / want_full_cd (calculateMetrics, :1147-1202).  world must be 1. */
 ME_API int  me_icp_point_to_point(me_ctx *ctx, double max_correspondence_distance, int32_t max_iteration,
                            double relative_fitness, double relative_rmse, const double T_init[16], me_icp_result *out);
+/* replaces: MapEval::performICPRegistration (map_eval.cpp:1366-1394), all three cases; method = param_.evaluation_method_
+ * (ME_ICP_*).  ME_ICP_POINT_TO_PLANE = RegistrationICP with TransformationEstimationPointToPlane: the ground-truth cloud
+ * needs normals (me_set_normals, e.g. from a PCD that carries them, or me_estimate_normals) — without them the call fails
+ * like Open3D does.  ME_ICP_GENERALIZED = RegistrationGeneralizedICP with TransformationEstimationForGeneralizedICP()
+ * (epsilon 1e-3): per-point covariances from EstimateNormals(KNN 20) on both clouds, computed inside.  Same post-condition
+ * as me_icp_point_to_point.  Normals handed in or estimated before the call do not survive ME_ICP_GENERALIZED. */
+ME_API int  me_icp(me_ctx *ctx, int32_t method, double max_correspondence_distance, int32_t max_iteration,
+                   double relative_fitness, double relative_rmse, const double T_init[16], me_icp_result *out);
+/* normals of a cloud held by the context, caller order, N x 3 fp64 (open3d PointCloud::normals_): upload / estimate as
+ * PointCloud::EstimateNormals(KDTreeSearchParamKNN(knn)) does (k nearest neighbours incl. the point, covariance, the
+ * eigenvector of the smallest eigenvalue; sign as Open3D's FastEigen3x3 leaves it) / read back.  me_transform rotates them. */
+ME_API int  me_set_normals(me_ctx *ctx, int which, const double *normals_host, int64_t n);
+ME_API int  me_estimate_normals(me_ctx *ctx, int which, int32_t knn);
+ME_API int  me_get_normals(me_ctx *ctx, int which, double *normals_host);
 /* builds (or rebuilds) the cell-sorted grid of one cloud; the eval calls build lazily if needed */
 ME_API int  me_build_grid(me_ctx *ctx, int which);
 

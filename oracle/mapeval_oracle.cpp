@@ -838,7 +838,9 @@ int oracle_icp_point_to_point(const double *est, int64_t n_est, const double *gt
   icp_evaluate(tree, pcd.data(), n_est, max_dist, res);
   int it = 0;
   for (; it < max_iter; ++it) {
-    if (res.n_corr == 0) break;      // Open3D would feed umeyama an empty set; nothing can be estimated
+    // TransformationEstimationPointToPoint::ComputeTransformation returns the identity for an empty correspondence set
+    double upd[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (res.n_corr > 0) {
     double ms[3] = {0, 0, 0}, md[3] = {0, 0, 0};
     for (int64_t i = 0; i < n_est; ++i)
       if (res.keep[i]) for (int a = 0; a < 3; ++a) { ms[a] += pcd[3 * i + a]; md[a] += gt[3ll * res.idx[i] + a]; }
@@ -853,10 +855,10 @@ int oracle_icp_point_to_point(const double *est, int64_t n_est, const double *gt
     double U[9], w[3], V[9], S[3] = {1, 1, 1};
     svd3_one_sided_jacobi(sigma, U, w, V);
     if (det3h(U) * det3h(V) < 0) S[2] = -1;
-    double upd[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) { double v = 0; for (int k = 0; k < 3; ++k) v += U[r * 3 + k] * S[k] * V[c * 3 + k]; upd[r * 4 + c] = v; }
     for (int r = 0; r < 3; ++r) upd[r * 4 + 3] = md[r] - (upd[r * 4] * ms[0] + upd[r * 4 + 1] * ms[1] + upd[r * 4 + 2] * ms[2]);
+    }
     double Tn[16];
     for (int r = 0; r < 4; ++r)
       for (int c = 0; c < 4; ++c) { double v = 0; for (int k = 0; k < 4; ++k) v += upd[r * 4 + k] * T[k * 4 + c]; Tn[r * 4 + c] = v; }

@@ -233,14 +233,38 @@ def test_map_eval_end_to_end(exe, tmp_path):
     np.testing.assert_array_equal(raw_rgb, _jet_u8(np.minimum(od2, 0.2) / 0.2))       # squared distance vs accuracy_level[0] (quirk)
     inl_pts, inl_rgb = _read_rendered(str(res_dir / "inlier_rendered_dis_map.pcd"))
     assert len(inl_pts) == onn.est_to_gt.n_corr
-    # evaluate_using_initial: false with generalized ICP (registration_methods: 2, the shipped default) is not provided
+    # evaluate_using_initial: false with generalized ICP (registration_methods: 2, what every shipped config sets):
+    # path B = RegistrationGeneralizedICP + calculateMetrics(reg)
     cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false"))
+    (est_dir / "map_results" / "map_results.txt").unlink()
     out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
-    assert out.returncode != 0 and "generalized ICP" in out.stderr
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = (est_dir / "map_results" / "map_results.txt").read_text().splitlines()
+    i0 = next(i for i, l in enumerate(res) if l.startswith("Aligned cloud:"))
+    Tm = np.array([[float(x) for x in res[i0].split(":", 1)[1].split()]] + [[float(x) for x in res[i0 + k].split()] for k in (1, 2, 3)])
+    Tg, fit, rmse, nc, it = O.icp_generalized(est, gt, 1.0)
+    np.testing.assert_allclose(Tm, Tg, atol=6e-6)                 # printed with setprecision(5)
+    line = {l.split(":")[0]: l.split(":", 1)[1].split() for l in res if ":" in l}
+    assert int(line["Aligned results"][1]) == nc and abs(float(line["Aligned results"][0]) - fit) < 6e-6
+    pb = A.make_nn_params([0.2, 0.1, 0.08, 0.05, 0.01], 1.0, cutoff_mode=A.ME_CUTOFF_DIST_LT_R, pairing=A.ME_PAIRING_GEOMETRIC)
+    ong = O.eval_nn(O.transform(est, Tg), gt, pb)
+    np.testing.assert_allclose([float(x) for x in line["RMSE/AC"]], list(ong.est_to_gt.rmse), rtol=1e-6, atol=1e-12)
+    # point-to-plane ICP needs normals in the ground-truth file (Open3D raises without them); an invalid method is
+    # rejected before map_results.txt is touched
+    (est_dir / "map_results" / "map_results.txt").unlink()
+    cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false")
+                    .replace("registration_methods: 2", "registration_methods: 1"))
+    out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
+    assert out.returncode != 0 and "requires pre-computed normal vectors" in out.stderr
+    (est_dir / "map_results" / "map_results.txt").unlink()
+    cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false")
+                    .replace("registration_methods: 2", "registration_methods: 7"))
+    out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
+    assert out.returncode != 0 and "Invalid registration type" in out.stderr
+    assert not (est_dir / "map_results" / "map_results.txt").exists()
     # ... point-to-point ICP (registration_methods: 0) is: path B = ICP + calculateMetrics(reg)
     cfgp.write_text(text.replace("evaluate_using_initial: true", "evaluate_using_initial: false")
                     .replace("registration_methods: 2", "registration_methods: 0"))
-    (est_dir / "map_results" / "map_results.txt").unlink()
     out = subprocess.run([exe, str(cfgp)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     res = (est_dir / "map_results" / "map_results.txt").read_text().splitlines()
