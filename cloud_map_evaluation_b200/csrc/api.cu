@@ -59,6 +59,8 @@ static void free_cloud(Cloud &c) {
   if (c.d_rel) cudaFree(c.d_rel);
   if (c.d_cell_off) cudaFree(c.d_cell_off);
   if (c.d_cell_id) cudaFree(c.d_cell_id);
+  if (c.d_hkey) cudaFree(c.d_hkey);
+  if (c.d_hval) cudaFree(c.d_hval);
   if (c.d_nn_idx) cudaFree(c.d_nn_idx);
   if (c.d_nn_d2) cudaFree(c.d_nn_d2);
   if (c.d_nn_sq) cudaFree(c.d_nn_sq);
@@ -144,6 +146,7 @@ void me_destroy(me_ctx *ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->d_work) cudaFree(ctx->d_work);
   if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
+  if (ctx->d_rs_hist) cudaFree(ctx->d_rs_hist);
   for (int i = 0; i < 2 * ME_N_STAGE_TIMES; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -32,8 +32,28 @@ struct Lattice {
   int nvox[3];       // voxels per axis
   int dims[3];       // cells per axis = nvox * m
   int nb[3];         // tiles (kTileEdge^3 cells) per axis
-  long long ncells;
+  long long ncells;  // dense table only
   long long nvoxels;
+  int sparse;        // 1: the cell table holds occupied row segments only (CellIndex below)
+  int nsegx;         // sparse: segments of kSegCells cells per lattice row = ceil(dims[0] / kSegCells)
+};
+
+// Cell table of a lattice = CSR offsets into the cell-sorted cloud, cells in (z, y, x) order, so that x-adjacent cells are
+// adjacent in the cloud and the run of cells [xa, xb] of one lattice row is one contiguous range of points.
+//   dense : off[c] for every cell c (ncells + 1 entries) — scenes whose bounding box fits the cell budget
+//   sparse: every lattice row is cut into segments of 32 cells along x; only OCCUPIED segments are stored, still in
+//           (z, y, x) order — off[rank * 32 + (x & 31)] — and an open-addressing hash table maps the segment key
+//           (row * nsegx + x / 32) to its rank.  Site-scale surface scans keep ~2 points per occupied cell whatever
+//           the extent; the point order, and with it every run-walking kernel, is the same as in the dense case.
+static constexpr int kSegCells = 32;
+struct CellIndex {
+  const uint32_t *off;
+  const unsigned long long *hkey;   // sparse: hash slots, ~0 = empty (linear probing)
+  const uint32_t *hval;             // rank of the segment
+  uint32_t hmask;                   // slots - 1
+  int nsegx;
+  int sparse;
+  int dimx, dimy, dimz;
 };
 
 struct Cloud {
@@ -51,8 +71,13 @@ struct Cloud {
   long long cap_sorted = 0;
   float4 *d_rel = nullptr;      // cell-sorted fp32 screening copy: xyz relative to the point's own cell origin, w = (float)ix
   long long cap_rel = 0;
-  uint32_t *d_cell_off = nullptr;   // ncells + 1 CSR offsets into d_sorted: cell c = [off[c], off[c+1])
+  uint32_t *d_cell_off = nullptr;   // dense: ncells + 1 CSR offsets into d_sorted: cell c = [off[c], off[c+1]); sparse: nseg * 32 + 1
   long long cap_cells = 0;
+  unsigned long long *d_hkey = nullptr;   // sparse lattice: segment hash table (CellIndex)
+  uint32_t *d_hval = nullptr;
+  long long cap_hash = 0;
+  uint32_t hmask = 0;
+  long long n_seg = 0;
   uint32_t *d_cell_id = nullptr;    // scratch: cell of each point (caller order)
   long long cap_cell_id = 0;
   uint32_t *d_tiles = nullptr;      // non-empty query tiles (tile id = (bz*nb[1]+by)*nb[0]+bx)
@@ -109,6 +134,8 @@ struct me_ctx {
   size_t work_bytes = 0;
   uint32_t *d_scan_tmp = nullptr;   // per-tile partials of exclusive_scan_inplace
   long long cap_scan_tmp = 0;
+  uint32_t *d_rs_hist = nullptr;    // radix sort: digit histograms of every tile
+  long long cap_rs_hist = 0;
   cudaEvent_t ev[2 * ME_N_STAGE_TIMES];
   bool ev_used[ME_N_STAGE_TIMES];
   int sm_count = 148;
@@ -156,6 +183,14 @@ struct StageTimer {
   ~StageTimer() { cudaEventRecord(ctx->ev[2 * stage + 1], ctx->stream); ctx->ev_used[stage] = true; }
 };
 
+inline CellIndex index_of(const Cloud &c) {
+  CellIndex I;
+  I.off = c.d_cell_off; I.hkey = c.d_hkey; I.hval = c.d_hval; I.hmask = c.hmask;
+  I.nsegx = c.lat.nsegx; I.sparse = c.lat.sparse;
+  I.dimx = c.lat.dims[0]; I.dimy = c.lat.dims[1]; I.dimz = c.lat.dims[2];
+  return I;
+}
+
 // stage entry points (implemented in grid.cu / nn.cu / mme.cu / voxel.cu)
 int wait_upload(me_ctx *ctx, int which);
 int compute_bbox(me_ctx *ctx, int which);
@@ -166,6 +201,8 @@ int build_tiles(me_ctx *ctx, int which);
 int query_shard(me_ctx *ctx, int which, long long *b, long long *e);
 int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n);
 int voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out);
+int radix_sort_pairs(me_ctx *ctx, unsigned long long *keys, uint32_t *vals, unsigned long long *keys_tmp, uint32_t *vals_tmp,
+                     long long n, int key_bits, unsigned long long **keys_sorted, uint32_t **vals_sorted);
 int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e);
 int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2);
 int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out);
@@ -225,6 +262,53 @@ __device__ __forceinline__ P4 load_p4(const P4 *p) {
   P4 r;
   r.x = a.x; r.y = a.y; r.z = b.x; r.idx = __double_as_longlong(b.y);
   return r;
+}
+
+// ---- cell table access -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t seg_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 29;
+  return (uint32_t)k;
+}
+__device__ __forceinline__ bool seg_find(const CellIndex &I, unsigned long long key, uint32_t &rank) {
+  uint32_t h = seg_hash(key) & I.hmask;
+  for (;;) {
+    const unsigned long long k = __ldg(I.hkey + h);
+    if (k == key) { rank = __ldg(I.hval + h); return true; }
+    if (k == ~0ull) return false;
+    h = (h + 1) & I.hmask;
+  }
+}
+// points of the cells [xa, xb] of lattice row (y, z): [s, e) of the sorted cloud; the caller keeps 0 <= xa <= xb < dimx
+// and the row inside the lattice
+__device__ __forceinline__ void cell_range(const CellIndex &I, int z, int y, int xa, int xb, uint32_t &s, uint32_t &e) {
+  if (!I.sparse) {
+    const uint32_t row = ((uint32_t)z * (uint32_t)I.dimy + (uint32_t)y) * (uint32_t)I.dimx;
+    s = __ldg(I.off + row + (uint32_t)xa);
+    e = __ldg(I.off + row + (uint32_t)xb + 1);
+    return;
+  }
+  const unsigned long long rowkey = ((unsigned long long)z * (unsigned long long)I.dimy + (unsigned long long)y) * (unsigned long long)I.nsegx;
+  const int ga = xa >> 5, gb = xb >> 5;
+  s = 0; e = 0;
+  bool have = false;
+  for (int g = ga; g <= gb; ++g) {
+    uint32_t r;
+    if (!seg_find(I, rowkey + (unsigned long long)g, r)) continue;
+    const uint32_t base = r << 5;
+    if (!have) { s = __ldg(I.off + base + (g == ga ? (uint32_t)(xa & 31) : 0u)); have = true; }
+    e = __ldg(I.off + base + (g == gb ? (uint32_t)(xb & 31) + 1u : 32u));
+  }
+}
+// lattice cell of a point of the sorted cloud from its tag (dense: the cell id; sparse: the row id z * dimy + y, the x
+// index comes from the cell-relative copy or from the coordinate)
+__device__ __forceinline__ void cell_from_tag(const CellIndex &I, long long tag, int ix_if_sparse, int &ix, int &iy, int &iz) {
+  const uint32_t t = cell_of(tag);
+  if (I.sparse) { ix = ix_if_sparse; iy = (int)(t % (uint32_t)I.dimy); iz = (int)(t / (uint32_t)I.dimy); }
+  else {
+    ix = (int)(t % (uint32_t)I.dimx);
+    const uint32_t cyz = t / (uint32_t)I.dimx;
+    iy = (int)(cyz % (uint32_t)I.dimy); iz = (int)(cyz / (uint32_t)I.dimy);
+  }
 }
 
 // order-preserving map double -> uint64 (for atomicMin/atomicMax on doubles)

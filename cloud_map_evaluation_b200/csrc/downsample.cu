@@ -9,10 +9,8 @@
 // increasing (ix, iy, iz).  The SET of output points is bit-identical to the CPU path: the 64-bit voxel keys are sorted
 // with a STABLE radix sort (points of a voxel stay in input order) and each voxel is summed sequentially by one thread.
 //
-// The sort is cub::DeviceRadixSort (CCCL, shipped with the CUDA toolkit): library code, used here because this
-// pre-step is outside the north-star hot path; key building, run detection and the ordered sums are kernels of ours.
+// The sort is the library's own LSD radix sort (sort.cu); key building, run detection and the ordered sums follow.
 #include "common.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 
 namespace me {
@@ -20,7 +18,7 @@ namespace me {
 static constexpr int kThreads = 256;
 static constexpr int kAxisBits = 21;      // voxel indices per axis < 2^21 (1 cm voxels: 20 km)
 
-struct VdsGeom { double org[3]; double s; };
+struct VdsGeom { double org[3]; double s; int bits[3]; };      // bits per axis of the packed key (from the extent)
 
 __global__ void __launch_bounds__(kThreads) vds_key_kernel(const double *__restrict__ xyz, long long n, VdsGeom g,
                                                            unsigned long long *__restrict__ key,
@@ -31,8 +29,8 @@ __global__ void __launch_bounds__(kThreads) vds_key_kernel(const double *__restr
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const double r = floor(__ddiv_rn(__dsub_rn(__ldg(xyz + 3 * i + a), g.org[a]), g.s));
-      ok = ok && r >= 0.0 && r < (double)(1 << kAxisBits);
-      k = (k << kAxisBits) | (unsigned long long)(ok ? (long long)r : 0ll);
+      ok = ok && r >= 0.0 && r < (double)(1ll << g.bits[a]);
+      k = (k << g.bits[a]) | (unsigned long long)(ok ? (long long)r : 0ll);
     }
     if (!ok) atomicAdd(bad, 1u);
     key[i] = k;
@@ -77,15 +75,24 @@ int voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out) 
   const long long n = c.n;
   VdsGeom g;
   g.s = voxel_size;
-  for (int a = 0; a < 3; ++a) g.org[a] = c.bbox_min[a] - voxel_size * 0.5;      // voxel_min_bound
+  int key_bits = 0;
+  for (int a = 0; a < 3; ++a) {
+    g.org[a] = c.bbox_min[a] - voxel_size * 0.5;      // voxel_min_bound
+    // voxels along this axis (+2 of slack for the rounding of the division): only as many key bits as the extent needs,
+    // so that the radix sort runs 4-5 passes instead of 8
+    const double nv_axis = std::floor((c.bbox_max[a] - g.org[a]) / voxel_size) + 3.0;
+    if (!(nv_axis < (double)(1 << kAxisBits)))
+      return fail(ctx, ME_ERR_RANGE, "voxel_size is too small for the extent of the cloud (more than 2^21 voxels per axis)");
+    int b = 1;
+    while ((1ll << b) < (long long)nv_axis) ++b;
+    g.bits[a] = b;
+    key_bits += b;
+  }
 
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
-                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 3 * kAxisBits, ctx->stream);
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_key0 = 256, o_key1 = o_key0 + align((size_t)n * 8), o_val0 = o_key1 + align((size_t)n * 8),
                o_val1 = o_val0 + align((size_t)n * 4), o_pos = o_val1 + align((size_t)n * 4),
-               o_cub = o_pos + align((size_t)(n + 1) * 4), total = o_cub + align(cub_bytes);
+               total = o_pos + align((size_t)(n + 1) * 4);
   ME_TRY(ensure_work(ctx, total));
   char *base = (char *)ctx->d_work;
   unsigned int *d_bad = (unsigned int *)base;
@@ -95,8 +102,10 @@ int voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out) 
   const int blocks = (int)std::min<long long>((n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
   vds_key_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, n, g, key0, val0, d_bad);
   ME_LAUNCH_CHECK(ctx);
-  ME_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_cub, cub_bytes, key0, key1, val0, val1, (int)n, 0, 3 * kAxisBits, ctx->stream));
-  ctx->launches += 2 * ((3 * kAxisBits + 7) / 8);     // the library's histogram / onesweep passes (approximate)
+  unsigned long long *key1s = nullptr;
+  uint32_t *val1s = nullptr;
+  ME_TRY(radix_sort_pairs(ctx, key0, val0, key1, val1, n, key_bits, &key1s, &val1s));      // stable
+  key1 = key1s; val1 = val1s;
   vds_head_kernel<<<blocks, kThreads, 0, ctx->stream>>>(key1, n, pos);
   ME_LAUNCH_CHECK(ctx);
   ME_TRY(exclusive_scan_inplace(ctx, pos, n + 1));

@@ -8,6 +8,7 @@
 // grids sized in multiples of the SM count, no tensor cores.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -295,6 +296,7 @@ int build_tiles(me_ctx *ctx, int which) {
   Cloud &c = ctx->cloud[which];
   if (c.tiles_valid) return ME_OK;
   const Lattice &L = c.lat;
+  if (L.sparse) return fail(ctx, ME_ERR_RANGE, "the tile sweep needs a dense cell table");
   const long long nt = (long long)L.nb[0] * L.nb[1] * L.nb[2];
   ME_TRY(ensure(ctx, (void **)&c.d_tiles, &c.cap_tiles, std::min<long long>(nt, c.n), sizeof(uint32_t)));
   ME_TRY(ensure(ctx, (void **)&c.d_tile_pos, &c.cap_tile_pos, nt + 1, sizeof(uint32_t)));
@@ -331,6 +333,11 @@ __global__ void shard_bounds_kernel(const P4 *__restrict__ sorted, const uint32_
 int query_shard(me_ctx *ctx, int which, long long *b, long long *e) {
   Cloud &c = ctx->cloud[which];
   if (ctx->world == 1) { *b = 0; *e = c.n; return ME_OK; }
+  if (c.lat.sparse) {      // the sparse build sorts stably: every rank holds the same order, no snapping needed
+    *b = c.n * ctx->rank / ctx->world;
+    *e = c.n * (ctx->rank + 1) / ctx->world;
+    return ME_OK;
+  }
   if (!(c.shard_valid && c.shard_rank == ctx->rank && c.shard_world == ctx->world)) {
     unsigned long long *d = (unsigned long long *)ctx->d_scratch + 12, *h = (unsigned long long *)ctx->h_pinned + 12;
     shard_bounds_kernel<<<1, 32, 0, ctx->stream>>>(c.d_sorted, c.d_cell_off, c.n, ctx->rank, ctx->world, d);
@@ -347,10 +354,15 @@ int query_shard(me_ctx *ctx, int which, long long *b, long long *e) {
 // ---------------------------------------------------------------------------------------------------------------
 // host: lattice choice
 // ---------------------------------------------------------------------------------------------------------------
-static bool make_lattice(const Cloud &c, double v, int m, long long budget, Lattice *out) {
+// sparse cell tables are used when the dense table would exceed the budget (test hook: ME_NO_SPARSE keeps the round-1
+// behaviour of coarsening the cells instead)
+static bool sparse_allowed() { return getenv("ME_NO_SPARSE") == nullptr; }
+
+static bool make_lattice(const Cloud &c, double v, int m, long long budget, Lattice *out, bool allow_sparse) {
   Lattice L;
   L.v = v; L.m = m; L.h = v / m; L.m_over_v = m / v;
-  long long nc = 1, nv = 1;
+  L.sparse = 0; L.nsegx = 0;
+  double nc = 1.0, nv = 1.0;
   for (int a = 0; a < 3; ++a) {
     double klo = std::floor(c.bbox_min[a] / v), khi = std::floor(c.bbox_max[a] / v);
     if (!(klo > -2.0e9 && khi < 2.0e9)) return false;   // the reference casts to int (voxel_calculator.cpp:242)
@@ -360,12 +372,22 @@ static bool make_lattice(const Cloud &c, double v, int m, long long budget, Latt
     L.nvox[a] = (int)nvx;
     L.dims[a] = L.nvox[a] * m;
     L.nb[a] = (L.dims[a] + kTileEdge - 1) / kTileEdge;
-    if ((double)nc * L.dims[a] > 4.0e9) return false;
-    nc *= L.dims[a];
-    nv *= L.nvox[a];
+    nc *= (double)L.dims[a];
+    nv *= nvx;
   }
-  if (nc > budget || nc >= 0xffffffffll) return false;
-  L.ncells = nc; L.nvoxels = nv;
+  L.nvoxels = nv < 9.0e18 ? (long long)nv : -1;         // the voxel stage checks its own (dense) table budget
+  if (nc <= (double)budget && nc < 4294967295.0) {
+    L.ncells = (long long)nc;
+    *out = L;
+    return true;
+  }
+  if (!allow_sparse) return false;
+  // sparse table: x indices live in an fp32 mantissa, row ids (z * dimy + y) in the 32-bit half of the point tag
+  if (L.dims[0] >= (1 << 24) || L.dims[1] >= (1 << 24) || L.dims[2] >= (1 << 24)) return false;
+  if ((double)L.dims[1] * (double)L.dims[2] >= 4294967295.0) return false;
+  L.sparse = 1;
+  L.nsegx = (L.dims[0] + kSegCells - 1) / kSegCells;
+  L.ncells = 0;
   *out = L;
   return true;
 }
@@ -405,13 +427,13 @@ double density_edge(const Cloud &c) {
 
 // (v, m) for a target cell edge, fitting `c` (and `other`, if its bbox is known) into the budget
 static bool pick_spec(const Cloud &c, const Cloud *other, double v_req, double h_target, long long budget, double *v,
-                      int *m, Lattice *out) {
+                      int *m, Lattice *out, bool allow_sparse) {
   Lattice tmp;
   if (v_req > 0) {
     int mm = (int)std::max(1.0, std::floor(v_req / h_target + 0.5));
     mm = std::min(mm, 1 << 20);
     for (; mm >= 1; --mm) {
-      if (make_lattice(c, v_req, mm, budget, out) && (!other || make_lattice(*other, v_req, mm, budget, &tmp))) {
+      if (make_lattice(c, v_req, mm, budget, out, allow_sparse) && (!other || make_lattice(*other, v_req, mm, budget, &tmp, allow_sparse))) {
         *v = v_req; *m = mm;
         return true;
       }
@@ -421,7 +443,7 @@ static bool pick_spec(const Cloud &c, const Cloud *other, double v_req, double h
   }
   double h = h_target;
   for (int t = 0; t < 96; ++t, h *= 1.26)
-    if (make_lattice(c, h, 1, budget, out) && (!other || make_lattice(*other, h, 1, budget, &tmp))) {
+    if (make_lattice(c, h, 1, budget, out, allow_sparse) && (!other || make_lattice(*other, h, 1, budget, &tmp, allow_sparse))) {
       *v = h; *m = 1;
       return true;
     }
@@ -447,9 +469,146 @@ int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
 // point: a 200 M-point surface scan at 1 cm spacing keeps ~4 points per occupied cell instead of ~18; the table then
 // takes 8.6 GB of the 180 GB and ~5 ms per build to clear and scan, against sweeps of hundreds of ms at that size).
 static long long grid_budget(const me_ctx *ctx) {
+  if (getenv("ME_FORCE_SPARSE")) return 1;      // test hook: every lattice gets a sparse cell table
   if (ctx->max_grid_cells > 0) return ctx->max_grid_cells;
   const long long n = std::max(ctx->cloud[0].n, ctx->cloud[1].n);
   return std::min<long long>(1ll << 31, std::max<long long>(1ll << 28, 16 * n));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sparse lattice build: points sorted by their 64-bit cell key (row * 32 nsegx + ix) with the library's radix sort, the
+// occupied row segments found as runs of the sorted keys, their 32-cell count blocks laid out in the same order (a CSR
+// table over occupied segments only) and entered into a hash table (segment key -> rank)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) sparse_key_kernel(const double *__restrict__ xyz, long long n, Lattice L,
+                                                              unsigned long long *__restrict__ key, uint32_t *__restrict__ val) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    long long ix = cell_coord(x, L, 0), iy = cell_coord(y, L, 1), iz = cell_coord(z, L, 2);
+    ix = ix < 0 ? 0 : (ix >= L.dims[0] ? L.dims[0] - 1 : ix);
+    iy = iy < 0 ? 0 : (iy >= L.dims[1] ? L.dims[1] - 1 : iy);
+    iz = iz < 0 ? 0 : (iz >= L.dims[2] ? L.dims[2] - 1 : iz);
+    const unsigned long long row = (unsigned long long)iz * (unsigned long long)L.dims[1] + (unsigned long long)iy;
+    key[i] = row * (unsigned long long)(L.nsegx * kSegCells) + (unsigned long long)ix;
+    val[i] = (uint32_t)i;
+  }
+}
+// head[i] = 1 where a new segment (key >> 5) starts in the sorted key sequence; head[n] = 0 (after the scan: segment count)
+__global__ void __launch_bounds__(kThreads) sparse_head_kernel(const unsigned long long *__restrict__ key, long long n,
+                                                               uint32_t *__restrict__ head) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= n; i += (long long)gridDim.x * blockDim.x)
+    head[i] = (i < n && (i == 0 || (key[i] >> 5) != (key[i - 1] >> 5))) ? 1u : 0u;
+}
+// per point: count into its cell of the compact table; per segment head: hash insert (segment key -> rank).
+// rank_excl = exclusive scan of the head flags: the segment of point i has rank rank_excl[i + 1] - 1.
+__global__ void __launch_bounds__(kThreads) sparse_count_kernel(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ rank_excl,
+                                                                long long n, uint32_t *__restrict__ count,
+                                                                unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hval,
+                                                                uint32_t hmask) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = key[i];
+    const uint32_t r = rank_excl[i + 1] - 1u;
+    atomicAdd(count + ((unsigned long long)r << 5) + (k & 31ull), 1u);
+    if (i == 0 || (key[i - 1] >> 5) != (k >> 5)) {      // the first point of a segment enters it into the hash table
+      const unsigned long long sk = k >> 5;
+      uint32_t h = seg_hash(sk) & hmask;
+      for (;;) {
+        const unsigned long long old = atomicCAS(hkey + h, ~0ull, sk);
+        if (old == ~0ull || old == sk) { hval[h] = r; break; }
+        h = (h + 1) & hmask;
+      }
+    }
+  }
+}
+// the sorted records and their fp32 screening copies, written in sorted order (gather from the caller-order array)
+__global__ void __launch_bounds__(kThreads) sparse_gather_kernel(const double *__restrict__ xyz, const unsigned long long *__restrict__ key,
+                                                                 const uint32_t *__restrict__ val, long long n, Lattice L,
+                                                                 P4 *__restrict__ sorted, float4 *__restrict__ rel) {
+  const unsigned long long rowlen = (unsigned long long)(L.nsegx * kSegCells);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = key[i];
+    const uint32_t o = val[i];
+    const unsigned long long row = k / rowlen;
+    const uint32_t ix = (uint32_t)(k - row * rowlen);
+    const uint32_t iy = (uint32_t)(row % (unsigned long long)L.dims[1]), iz = (uint32_t)(row / (unsigned long long)L.dims[1]);
+    const double x = __ldg(xyz + 3ll * o), y = __ldg(xyz + 3ll * o + 1), z = __ldg(xyz + 3ll * o + 2);
+    double2 *out = reinterpret_cast<double2 *>(sorted + i);
+    out[0] = make_double2(x, y);
+    out[1] = make_double2(z, __longlong_as_double((long long)((row << 32) | (unsigned long long)o)));      // tag: row id | caller index
+    rel[i] = make_float4((float)cell_rel(x, ix, L, 0), (float)cell_rel(y, iy, L, 1), (float)cell_rel(z, iz, L, 2), (float)ix);
+  }
+}
+__global__ void fill_u64_kernel(unsigned long long *p, long long n, unsigned long long v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// lays `c` out on the sparse lattice L; *occupied = cells that hold at least one point
+static int build_sparse(me_ctx *ctx, Cloud &c, const Lattice &L, long long *occupied) {
+  const long long n = c.n;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_key0 = 0, o_key1 = o_key0 + align((size_t)n * 8), o_val0 = o_key1 + align((size_t)n * 8),
+               o_val1 = o_val0 + align((size_t)n * 4), o_rank = o_val1 + align((size_t)n * 4), total = o_rank + align((size_t)(n + 1) * 4);
+  ME_TRY(ensure_work(ctx, total));
+  char *base = (char *)ctx->d_work;
+  unsigned long long *key0 = (unsigned long long *)(base + o_key0), *key1 = (unsigned long long *)(base + o_key1);
+  uint32_t *val0 = (uint32_t *)(base + o_val0), *val1 = (uint32_t *)(base + o_val1), *rank = (uint32_t *)(base + o_rank);
+  const int blocks = (int)std::min<long long>((n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  sparse_key_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, n, L, key0, val0);
+  ME_LAUNCH_CHECK(ctx);
+  int key_bits = 1;
+  const double kmax = (double)L.dims[1] * (double)L.dims[2] * (double)(L.nsegx * kSegCells);
+  while (key_bits < 63 && std::ldexp(1.0, key_bits) < kmax) ++key_bits;
+  unsigned long long *keys = nullptr;
+  uint32_t *vals = nullptr;
+  ME_TRY(radix_sort_pairs(ctx, key0, val0, key1, val1, n, key_bits, &keys, &vals));      // stable: points of a cell keep the caller's order
+  sparse_head_kernel<<<blocks, kThreads, 0, ctx->stream>>>(keys, n, rank);
+  ME_LAUNCH_CHECK(ctx);
+  ME_TRY(exclusive_scan_inplace(ctx, rank, n + 1));
+  uint32_t *h_nseg = (uint32_t *)((unsigned long long *)ctx->h_pinned + 8);
+  ME_CUDA(ctx, cudaMemcpyAsync(h_nseg, rank + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const long long nseg = (long long)*h_nseg;
+  if (nseg * kSegCells >= 0xffffffffll) return fail(ctx, ME_ERR_RANGE, "sparse lattice: more than 2^27 occupied row segments");
+  long long slots = 1;
+  while (slots < 2 * nseg) slots <<= 1;
+  ME_TRY(ensure(ctx, (void **)&c.d_cell_off, &c.cap_cells, nseg * kSegCells + 1, sizeof(uint32_t)));
+  if (!(c.d_hkey && c.cap_hash >= slots)) {
+    if (c.d_hkey) cudaFree(c.d_hkey);
+    if (c.d_hval) cudaFree(c.d_hval);
+    c.d_hkey = nullptr; c.d_hval = nullptr; c.cap_hash = 0;
+    long long cap = 0;
+    ME_TRY(ensure(ctx, (void **)&c.d_hkey, &cap, slots, sizeof(unsigned long long)));
+    cap = 0;
+    ME_TRY(ensure(ctx, (void **)&c.d_hval, &cap, slots, sizeof(uint32_t)));
+    c.cap_hash = slots;
+  }
+  c.hmask = (uint32_t)(slots - 1);
+  c.n_seg = nseg;
+  ME_CUDA(ctx, cudaMemsetAsync(c.d_cell_off, 0, (size_t)(nseg * kSegCells + 1) * sizeof(uint32_t), ctx->stream));
+  fill_u64_kernel<<<(int)std::min<long long>((slots + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16), kThreads, 0, ctx->stream>>>(c.d_hkey, slots, ~0ull);
+  ME_LAUNCH_CHECK(ctx);
+  // count of compact cell k at off[k]; the exclusive scan over the ncomp + 1 entries (the last one zero) makes it a CSR array
+  sparse_count_kernel<<<blocks, kThreads, 0, ctx->stream>>>(keys, rank, n, c.d_cell_off, c.d_hkey, c.d_hval, c.hmask);
+  ME_LAUNCH_CHECK(ctx);
+  unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
+  ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  {
+    const long long ncomp = nseg * kSegCells;
+    const int ob = (int)std::min<long long>((ncomp + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+    occupancy_kernel<<<ob, kThreads, 0, ctx->stream>>>(c.d_cell_off, ncomp, d_nt + 1);
+    ME_LAUNCH_CHECK(ctx);
+  }
+  unsigned long long *h_nt = (unsigned long long *)ctx->h_pinned + 8;
+  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_TRY(exclusive_scan_inplace(ctx, c.d_cell_off, nseg * kSegCells + 1));
+  ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, n, sizeof(P4)));
+  ME_TRY(ensure(ctx, (void **)&c.d_rel, &c.cap_rel, n, sizeof(float4)));
+  sparse_gather_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, keys, vals, n, L, c.d_sorted, c.d_rel);
+  ME_LAUNCH_CHECK(ctx);
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *occupied = (long long)h_nt[1];
+  c.max_cell_count = (long long)h_nt[2];
+  return ME_OK;
 }
 
 // solo_h > 0: lay the cloud out on a lattice of its own with cells of (about) that edge — used by the MME sweep when the
@@ -467,18 +626,25 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
   ME_TRY(compute_bbox(ctx, which));
   const long long budget = grid_budget(ctx);
   const double v_req = ctx->voxel_hint;
+  const bool sp = sparse_allowed();
 
   // Both clouds share one lattice spec (v, m) so that their cells coincide.  The spec is re-planned whenever no
   // valid grid depends on it (i.e. at the first build of a pass); a later build re-uses it.
+  // A cloud whose dense cell table would exceed the budget at the wanted cell edge gets a SPARSE table at that edge
+  // (occupied row segments only) instead of coarser cells.
   Lattice L;
+  bool built = false;      // the sparse build lays the cloud out while planning
+  long long occupied = 0;
   if (solo) {
     double v; int m;
-    if (!pick_spec(c, nullptr, 0.0, solo_h, budget, &v, &m, &L))
-      return fail(ctx, ME_ERR_RANGE, "cannot fit the cloud into the dense lattice budget");
-    ME_TRY(histogram(ctx, c, L));
+    if (!pick_spec(c, nullptr, 0.0, solo_h, budget, &v, &m, &L, sp))
+      return fail(ctx, ME_ERR_RANGE, "cannot fit the cloud into the lattice");
+    if (L.sparse) { ME_TRY(build_sparse(ctx, c, L, &occupied)); built = true; }
+    else ME_TRY(histogram(ctx, c, L));
   } else if (o.grid_valid && !o.grid_solo && ctx->spec_m > 0 && (v_req <= 0 || ctx->spec_v == v_req) &&
-             make_lattice(c, ctx->spec_v, ctx->spec_m, budget, &L)) {
-    ME_TRY(histogram(ctx, c, L));
+             make_lattice(c, ctx->spec_v, ctx->spec_m, budget, &L, sp)) {
+    if (L.sparse) { ME_TRY(build_sparse(ctx, c, L, &occupied)); built = true; }
+    else ME_TRY(histogram(ctx, c, L));
   } else {
     if (o.grid_valid && !o.grid_solo) {   // the other grid's spec cannot host this cloud: both are laid out again
       o.grid_valid = false; o.nn_valid = false; o.entropy_valid = false;
@@ -489,16 +655,24 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     for (int iter = 0; iter < 4; ++iter) {
       Lattice cand;
       double v; int m;
-      if (!pick_spec(c, other, v_req, h_target, budget, &v, &m, &cand))
-        return fail(ctx, ME_ERR_RANGE, v_req > 0 ? "voxel size too small for the dense lattice budget (raise max_grid_cells)"
-                                                 : "cannot fit the cloud into the dense lattice budget");
-      if (have && cand.ncells == L.ncells && cand.m == L.m && cand.v == L.v) break;   // refinement changed nothing
+      // dense first; if the budget forces cells noticeably coarser than wanted, a sparse table at the wanted edge instead
+      bool ok = pick_spec(c, other, v_req, h_target, budget, &v, &m, &cand, false);
+      if (sp && (!ok || cand.h > 1.25 * h_target)) {
+        Lattice cs;
+        double vs; int ms;
+        if (pick_spec(c, other, v_req, h_target, budget, &vs, &ms, &cs, true)) { cand = cs; v = vs; m = ms; ok = true; }
+      }
+      if (!ok)
+        return fail(ctx, ME_ERR_RANGE, v_req > 0 ? "voxel size too small for the lattice (dense budget and sparse limits exceeded)"
+                                                 : "cannot fit the cloud into the lattice");
+      if (have && cand.sparse == L.sparse && cand.m == L.m && cand.v == L.v && cand.dims[0] == L.dims[0]) break;   // refinement changed nothing
       L = cand; have = true;
       ctx->spec_v = v; ctx->spec_m = m;
-      ME_TRY(histogram(ctx, c, L));
+      long long max_count = 0;
+      if (L.sparse) { ME_TRY(build_sparse(ctx, c, L, &occupied)); built = true; }
+      else { built = false; ME_TRY(histogram(ctx, c, L)); }
       if (ctx->nn_cell_size > 0) break;   // caller fixed the cell size
-      long long occupied = 0, max_count = 0;
-      ME_TRY(occupancy(ctx, c, L, &occupied, &max_count));
+      if (!L.sparse) ME_TRY(occupancy(ctx, c, L, &occupied, &max_count));
       const double mean_occ = (double)c.n / (double)std::max<long long>(1, occupied);
       if (mean_occ <= 4.0 || iter == 3) break;
       // surface-like data: occupancy of occupied cells scales ~h^2; aim at ~2 points per occupied cell
@@ -511,29 +685,31 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
   c.solo_h = solo ? solo_h : 0.0;
   c.lat = L;
 
-  // scratch slots: [9] occupied cells, [10] largest cell (bounds the run lengths of the sweeps)
-  unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
-  ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, 3 * sizeof(unsigned long long), ctx->stream));
-  {
-    const int blocks = (int)std::min<long long>((L.ncells + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-    occupancy_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, d_nt + 1);
+  if (!built) {
+    // scratch slots: [9] occupied cells, [10] largest cell (bounds the run lengths of the sweeps)
+    unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
+    ME_CUDA(ctx, cudaMemsetAsync(d_nt, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    {
+      const int blocks = (int)std::min<long long>((L.ncells + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+      occupancy_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, d_nt + 1);
+      ME_LAUNCH_CHECK(ctx);
+    }
+    unsigned long long *h_nt = (unsigned long long *)ctx->h_pinned + 8;
+    ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+
+    // exclusive scan of the histogram, in place
+    ME_TRY(exclusive_scan_inplace(ctx, c.d_cell_off + 1, L.ncells));
+
+    ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, c.n, sizeof(P4)));
+    ME_TRY(ensure(ctx, (void **)&c.d_rel, &c.cap_rel, c.n, sizeof(float4)));
+    int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+    scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
     ME_LAUNCH_CHECK(ctx);
+    rel_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.n, L, c.d_rel);
+    ME_LAUNCH_CHECK(ctx);
+    ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    c.max_cell_count = (long long)h_nt[2];
   }
-  unsigned long long *h_nt = (unsigned long long *)ctx->h_pinned + 8;
-  ME_CUDA(ctx, cudaMemcpyAsync(h_nt, d_nt, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-
-  // exclusive scan of the histogram, in place
-  ME_TRY(exclusive_scan_inplace(ctx, c.d_cell_off + 1, L.ncells));
-
-  ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, c.n, sizeof(P4)));
-  ME_TRY(ensure(ctx, (void **)&c.d_rel, &c.cap_rel, c.n, sizeof(float4)));
-  int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-  scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
-  ME_LAUNCH_CHECK(ctx);
-  rel_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.n, L, c.d_rel);
-  ME_LAUNCH_CHECK(ctx);
-  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  c.max_cell_count = (long long)h_nt[2];
   c.tiles_valid = false;
   c.shard_valid = false;
   c.grid_valid = true;

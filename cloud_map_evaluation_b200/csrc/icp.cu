@@ -259,16 +259,18 @@ __device__ void fast_eigen3x3_normal(const double cov[9], double nrm[3]) {
 static constexpr int kKnnThreads = 128;
 
 __global__ void __launch_bounds__(kKnnThreads)
-knn_normals_kernel(const P4 *__restrict__ S, long long n, const uint32_t *__restrict__ cell_off, Lattice L, int k, double slack,
+knn_normals_kernel(const P4 *__restrict__ S, long long n, CellIndex I, Lattice L, int k, double slack,
                    int gicp, double *__restrict__ normals) {
   extern __shared__ __align__(16) unsigned char knn_smem[];
   double *dk = reinterpret_cast<double *>(knn_smem) + threadIdx.x;                                     // dk[t * kKnnThreads]
   uint32_t *ik = reinterpret_cast<uint32_t *>(knn_smem + (size_t)k * kKnnThreads * sizeof(double)) + threadIdx.x;
   for (long long i = blockIdx.x * (long long)kKnnThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kKnnThreads) {
     const P4 q = load_p4(S + i);
-    const unsigned int cq = cell_of(q.idx);
-    const long long ix = cq % (unsigned int)L.dims[0], iy = (cq / (unsigned int)L.dims[0]) % (unsigned int)L.dims[1],
-                    iz = cq / ((unsigned int)L.dims[0] * (unsigned int)L.dims[1]);
+    int cix, ciy, ciz;
+    long long xs = I.sparse ? cell_coord(q.x, L, 0) : 0;
+    xs = xs < 0 ? 0 : (xs >= L.dims[0] ? L.dims[0] - 1 : xs);
+    cell_from_tag(I, q.idx, (int)xs, cix, ciy, ciz);
+    const long long ix = cix, iy = ciy, iz = ciz;
     int cnt = 0;
     double kth = INFINITY;
     for (int r = 0;; ++r) {
@@ -278,7 +280,6 @@ knn_normals_kernel(const P4 *__restrict__ S, long long n, const uint32_t *__rest
         for (int dy = -r; dy <= r; ++dy) {
           const long long y = iy + dy;
           if (y < 0 || y >= L.dims[1]) continue;
-          const long long row = (z * L.dims[1] + y) * (long long)L.dims[0];
           const bool border = (dz == -r || dz == r || dy == -r || dy == r);
           for (int part = 0; part < 2; ++part) {
             long long xa, xb;
@@ -286,7 +287,8 @@ knn_normals_kernel(const P4 *__restrict__ S, long long n, const uint32_t *__rest
             else { xa = xb = part ? ix + r : ix - r; }
             xa = max(xa, 0ll); xb = min(xb, (long long)L.dims[0] - 1);
             if (xa > xb) continue;
-            const uint32_t s = __ldg(cell_off + row + xa), e = __ldg(cell_off + row + xb + 1);
+            uint32_t s, e;
+            cell_range(I, (int)z, (int)y, (int)xa, (int)xb, s, e);
             for (uint32_t j = s; j < e; ++j) {
               const P4 p = load_p4(S + j);
               const double d2 = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z);
@@ -355,7 +357,7 @@ int estimate_normals(me_ctx *ctx, int which, int knn, int gicp) {
   for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(c.bbox_min[a]), std::fabs(c.bbox_max[a])));
   const double slack = 1e-9 * c.lat.h + 4e-14 * maxabs;
   const int blocks = (int)std::min<long long>((c.n + kKnnThreads - 1) / kKnnThreads, (long long)ctx->sm_count * 32);
-  knn_normals_kernel<<<blocks, kKnnThreads, smem, ctx->stream>>>(c.d_sorted, c.n, c.d_cell_off, c.lat, k, slack, gicp, c.d_normal);
+  knn_normals_kernel<<<blocks, kKnnThreads, smem, ctx->stream>>>(c.d_sorted, c.n, index_of(c), c.lat, k, slack, gicp, c.d_normal);
   ME_LAUNCH_CHECK(ctx);
   c.normal_valid = true;
   return ME_OK;

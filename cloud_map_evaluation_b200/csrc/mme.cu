@@ -101,12 +101,14 @@ __device__ void flush_stats(ThreadStats &t, MmeAcc *acc) {
 }
 
 // the radius walk of one query over the cell-sorted cloud
-__device__ __forceinline__ void walk_global(const P4 &q, const P4 *__restrict__ S, const uint32_t *__restrict__ cell_off,
+__device__ __forceinline__ void walk_global(const P4 &q, const P4 *__restrict__ S, const CellIndex &I,
                                             const Lattice &L, double r2, float rc2, int rings, Moments &m) {
-  // the query's own cell comes with its record (high half of the tag)
-  const unsigned int cq = cell_of(q.idx);
-  const long long ix = cq % (unsigned int)L.dims[0], iy = (cq / (unsigned int)L.dims[0]) % (unsigned int)L.dims[1],
-                  iz = cq / ((unsigned int)L.dims[0] * (unsigned int)L.dims[1]);
+  // the query's own cell comes with its record (high half of the tag; the x index of a sparse lattice from the coordinate)
+  int cix, ciy, ciz;
+  long long xs = I.sparse ? cell_coord(q.x, L, 0) : 0;
+  xs = xs < 0 ? 0 : (xs >= L.dims[0] ? L.dims[0] - 1 : xs);
+  cell_from_tag(I, q.idx, (int)xs, cix, ciy, ciz);
+  const long long ix = cix, iy = ciy, iz = ciz;
   const float ux = (float)(cell_coord_cont(q.x, L, 0) - (double)ix), uy = (float)(cell_coord_cont(q.y, L, 1) - (double)iy),
               uz = (float)(cell_coord_cont(q.z, L, 2) - (double)iz);   // position inside the own cell, [0,1)
   for (int dz = -rings; dz <= rings; ++dz) {
@@ -125,8 +127,8 @@ __device__ __forceinline__ void walk_global(const P4 &q, const P4 *__restrict__ 
       const int da = max((int)floorf(ux - xw), -rings), db = min((int)floorf(ux + xw), rings);
       const long long xa = max(ix + da, 0ll), xb = min(ix + db, (long long)L.dims[0] - 1);
       if (xa > xb) continue;
-      const long long row = (z * L.dims[1] + y) * (long long)L.dims[0];
-      const uint32_t s = __ldg(cell_off + row + xa), e = __ldg(cell_off + row + xb + 1);
+      uint32_t s, e;
+      cell_range(I, (int)z, (int)y, (int)xa, (int)xb, s, e);
       for (uint32_t j = s; j < e; ++j) {
         const P4 p = load_p4(S + j);
         const double dx = __dsub_rn(q.x, p.x), dy2 = __dsub_rn(q.y, p.y), dz2 = __dsub_rn(q.z, p.z);
@@ -143,7 +145,7 @@ __device__ __forceinline__ void walk_global(const P4 &q, const P4 *__restrict__ 
 // queries out tile by tile instead costs 20 %)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-mme_kernel(const P4 *__restrict__ S, long long q_begin, long long q_end, const uint32_t *__restrict__ cell_off,
+mme_kernel(const P4 *__restrict__ S, long long q_begin, long long q_end, CellIndex I,
            Lattice L, double r2, float rc2, int rings, int min_neighbors, double *__restrict__ entropy_sorted,
            MmeAcc *__restrict__ acc) {
   ThreadStats ts;
@@ -153,7 +155,7 @@ mme_kernel(const P4 *__restrict__ S, long long q_begin, long long q_end, const u
     const P4 q = load_p4(S + i);
     Moments m;
     m.init();
-    walk_global(q, S, cell_off, L, r2, rc2, rings, m);
+    walk_global(q, S, I, L, r2, rc2, rings, m);
     entropy_sorted[i] = finish_entropy(m, min_neighbors, ts);
   }
   flush_stats(ts, acc);
@@ -194,7 +196,7 @@ template <int R, bool E16, int U2>      // U2: 0 plain walk, 1 two candidates (t
 // 8 CTAs/SM at R <= 2 (64 registers, two spilled doubles): 4.62 -> 4.44 ms on C3; at R = 3 the 49-row table bounds it at 4
 __global__ void __launch_bounds__(kFlatThreads, (R <= 2 ? 8 : 4))
 mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
-                const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
+                CellIndex I, MmeConst C, double *__restrict__ entropy_sorted,
                 MmeAcc *__restrict__ acc) {
   extern __shared__ __align__(16) unsigned char flat_smem[];
   RunTab<E16> T(flat_smem);
@@ -207,7 +209,7 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
     const float4 qr = __ldg(rel + i);
     const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + i) + 3)));
     const int ix = (int)qr.w;
-    const uint32_t cyz = cq / (uint32_t)C.dimx;
+    const uint32_t cyz = I.sparse ? cq : cq / (uint32_t)C.dimx;
     const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
     const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
     float gl[R], gr[R];      // squared gaps to the d-th cell on the left / right along x (increasing in d)
@@ -228,11 +230,7 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
         for (int d = 0; d < R; ++d) { da -= (gl[d] <= rem) ? 1 : 0; db += (gr[d] <= rem) ? 1 : 0; }
         const int xa = max(ix + da, 0), xb = min(ix + db, C.dimx - 1);
         uint32_t s = 0, e = 0;
-        if ((unsigned)z < (unsigned)C.dimz && (unsigned)y < (unsigned)C.dimy && rem >= 0.f) {
-          const uint32_t row = ((uint32_t)z * (uint32_t)C.dimy + (uint32_t)y) * (uint32_t)C.dimx;
-          s = __ldg(cell_off + row + xa);
-          e = __ldg(cell_off + row + xb + 1);
-        }
+        if ((unsigned)z < (unsigned)C.dimz && (unsigned)y < (unsigned)C.dimy && rem >= 0.f) cell_range(I, z, y, xa, xb, s, e);
         if (e > s) { T.put(nrun, tid, s, e, dy + R, dz + R, (float)dy * h - qr.y, czv); ++nrun; }
       }
     }
@@ -312,7 +310,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 template <int R, int CAP, int U>      // CAP ring slots per thread, U candidates per inner iteration
 __global__ void __launch_bounds__(kRowsThreads, (R <= 2 ? 6 : 5))
 mme_rows_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
-                const uint32_t *__restrict__ cell_off, MmeConst C, double *__restrict__ entropy_sorted,
+                CellIndex I, MmeConst C, double *__restrict__ entropy_sorted,
                 MmeAcc *__restrict__ acc) {
   constexpr int NS = 2 * R + 1;
   constexpr uint32_t kSlot = kRowsThreads * sizeof(uint4);      // bytes between two slots of one thread
@@ -334,7 +332,7 @@ mme_rows_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
     const float4 qr = __ldg(rel + il);
     const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + il) + 3)));
     const int ix = (int)qr.w;
-    const uint32_t cyz = cq / (uint32_t)C.dimx;
+    const uint32_t cyz = I.sparse ? cq : cq / (uint32_t)C.dimx;
     const int iy = (int)(cyz % (uint32_t)C.dimy), iz = live ? (int)(cyz / (uint32_t)C.dimy) : -1000000;
     const float ux = qr.x * C.inv_h;
     {
@@ -379,9 +377,7 @@ mme_rows_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
         const float xw = sqrt_approx(rem) + 1e-3f;
         const int da = min(R, (int)(xw - ux + 1.f)), db = min(R, (int)(xw + ux));
         const int xa = max(ix - da, 0), xb = min(ix + db, C.dimx - 1);
-        const uint32_t row = ((uint32_t)z * (uint32_t)C.dimy + (uint32_t)y) * (uint32_t)C.dimx;
-        s = __ldg(cell_off + row + xa);
-        e = __ldg(cell_off + row + xb + 1);
+        cell_range(I, z, y, xa, xb, s, e);
       }
       const int len = (int)(e - s);
       const int maxlen = __reduce_max_sync(FULL, len);
@@ -422,7 +418,7 @@ static int launch_rows_v(me_ctx *ctx, Cloud &c, long long qb, long long qe, cons
   if (smem > 48 * 1024)
     ME_CUDA(ctx, cudaFuncSetAttribute(mme_rows_kernel<R, CAP, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int blocks = (int)std::min<long long>((qe - qb + kRowsThreads - 1) / kRowsThreads, (long long)ctx->sm_count * 192);
-  mme_rows_kernel<R, CAP, U><<<blocks, kRowsThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, c.d_entropy, acc);
+  mme_rows_kernel<R, CAP, U><<<blocks, kRowsThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, index_of(c), C, c.d_entropy, acc);
   ME_LAUNCH_CHECK(ctx);
   return ME_OK;
 }
@@ -447,7 +443,7 @@ static constexpr int kMaxPlaneRings = 15;
 
 __global__ void __launch_bounds__(kFlatThreads)
 mme_plane_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
-                 const uint32_t *__restrict__ cell_off, MmeConst C, int R, double *__restrict__ entropy_sorted,
+                 CellIndex I, MmeConst C, int R, double *__restrict__ entropy_sorted,
                  MmeAcc *__restrict__ acc) {
   extern __shared__ __align__(16) unsigned char flat_smem[];
   uint2 *tab = reinterpret_cast<uint2 *>(flat_smem);      // [slot][thread] {begin, len << 8 | dy + R}
@@ -460,7 +456,7 @@ mme_plane_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long 
     const float4 qr = __ldg(rel + i);
     const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + i) + 3)));
     const int ix = (int)qr.w;
-    const uint32_t cyz = cq / (uint32_t)C.dimx;
+    const uint32_t cyz = I.sparse ? cq : cq / (uint32_t)C.dimx;
     const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
     const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
     Moments m;
@@ -479,8 +475,8 @@ mme_plane_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long 
           const float xw = sqrtf(rem) + 1e-3f;
           const int da = -min(R, max(0, (int)floorf(xw - ux + 1.f))), db = min(R, max(0, (int)floorf(xw + ux)));
           const int xa = max(ix + da, 0), xb = min(ix + db, C.dimx - 1);
-          const uint32_t row = ((uint32_t)z * (uint32_t)C.dimy + (uint32_t)y) * (uint32_t)C.dimx;
-          const uint32_t s = __ldg(cell_off + row + xa), e = __ldg(cell_off + row + xb + 1);
+          uint32_t s, e;
+          cell_range(I, z, y, xa, xb, s, e);
           if (e > s) { tab[nrun * kFlatThreads + tid] = make_uint2(s, ((e - s) << 8) | (uint32_t)(dy + R)); ++nrun; }
         }
       }
@@ -529,7 +525,7 @@ mme_plane_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long 
 static int launch_plane(me_ctx *ctx, Cloud &c, long long qb, long long qe, const MmeConst &C, int rings, MmeAcc *acc) {
   const size_t smem = (size_t)(2 * rings + 1) * kFlatThreads * sizeof(uint2);
   const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 64);
-  mme_plane_kernel<<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, rings, c.d_entropy, acc);
+  mme_plane_kernel<<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, index_of(c), C, rings, c.d_entropy, acc);
   ME_LAUNCH_CHECK(ctx);
   return ME_OK;
 }
@@ -546,7 +542,7 @@ static int launch_flat(me_ctx *ctx, Cloud &c, long long qb, long long qe, const 
     ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // fine-grained grid (~2 queries per thread): 64 CTAs/SM -> 4.83 ms, 256 -> 4.62 ms, 1024 -> 4.67 ms
   const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 256);
-  mme_flat_kernel<R, E16, U2><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, c.d_cell_off, C, c.d_entropy, acc);
+  mme_flat_kernel<R, E16, U2><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, index_of(c), C, c.d_entropy, acc);
   ME_LAUNCH_CHECK(ctx);
   return ME_OK;
 }
@@ -627,7 +623,7 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
       else ME_TRY(launch_plane(ctx, c, qb, qe, C, rings, acc));
     } else {
       const int blocks = (int)std::min<long long>((qe - qb + kThreads - 1) / kThreads, (long long)ctx->sm_count * 64);
-      mme_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, qb, qe, c.d_cell_off, c.lat, radius * radius, rc2, rings,
+      mme_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, qb, qe, index_of(c), c.lat, radius * radius, rc2, rings,
                                                       min_neighbors, c.d_entropy, acc);
       ME_LAUNCH_CHECK(ctx);
     }

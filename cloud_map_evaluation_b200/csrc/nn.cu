@@ -387,6 +387,7 @@ nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lat
 // ---------------------------------------------------------------------------------------------------------------
 struct FlatGeom {
   int qdimx, qdimy;            // query lattice (to decode the query's cell)
+  int q_sparse;                // the query cloud's tag holds the row id (sparse table) instead of the cell id
   int rdimx, rdimy, rdimz;     // reference lattice
   long long shx, shy, shz;     // reference cell = query cell + shift (the lattices share v and m)
   float h;                     // cell edge
@@ -398,7 +399,7 @@ template <bool E16, int U2>      // U2: 0 plain walk, 1 two candidates (two load
 // 8 CTAs/SM: 1.38 / 1.76 ms on C3; 10: 1.47 / 1.85; 12: 1.56 / 1.95 (spills + less L1)
 __global__ void __launch_bounds__(kFlatThreads, 8)
 nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
-               const P4 *__restrict__ R, const float4 *__restrict__ rrel, const uint32_t *__restrict__ r_off,
+               const P4 *__restrict__ R, const float4 *__restrict__ rrel, CellIndex Ir,
                Lattice Lr, FlatGeom G, NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
                double *__restrict__ nn_sq, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count) {
   __shared__ __align__(16) unsigned char tab_smem[9 * kFlatThreads * RunTab<E16>::kEntryBytes];
@@ -410,7 +411,7 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
     const float4 qr = __ldg(qrel + i);
     const P4 q = load_p4(Q + i);      // needed after the walk only; issued here so its latency hides behind the walk
     const uint32_t cq = cell_of(q.idx);
-    const uint32_t cyz = cq / (uint32_t)G.qdimx;
+    const uint32_t cyz = G.q_sparse ? cq : cq / (uint32_t)G.qdimx;      // row id z * dimy + y of the query's own lattice
     // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
     const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
                     cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
@@ -424,11 +425,7 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
       for (int dy = -1; dy <= 1; ++dy) {
         const long long y = cy + dy;
         uint32_t s = 0, e = 0;
-        if (z >= 0 && z < G.rdimz && y >= 0 && y < G.rdimy && xa <= xb) {
-          const uint32_t row = ((uint32_t)z * (uint32_t)G.rdimy + (uint32_t)y) * (uint32_t)G.rdimx;
-          s = __ldg(r_off + row + (uint32_t)xa);
-          e = __ldg(r_off + row + (uint32_t)xb + 1);
-        }
+        if (z >= 0 && z < G.rdimz && y >= 0 && y < G.rdimy && xa <= xb) cell_range(Ir, (int)z, (int)y, (int)xa, (int)xb, s, e);
         if (e > s) { T.put(nrun, tid, s, e, dy + 1, dz + 1, (float)dy * h - qr.y, czv); ++nrun; }
       }
     }
@@ -496,7 +493,7 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
 // far queries: one warp per query, Chebyshev rings r = 0, 1, 2, ... until the best beats the block faces
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, const uint32_t *__restrict__ cell_off, Lattice L,
+nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, Lattice L,
               NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
               const uint32_t *__restrict__ far_list, const unsigned int *__restrict__ far_count,
               AccBlock *__restrict__ acc) {
@@ -521,7 +518,6 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, const uint32_t
         const int dz = t / side - r, dy = t % side - r;
         const long long z = iz + dz, y = iy + dy;
         if (z < 0 || z >= L.dims[2] || y < 0 || y >= L.dims[1]) continue;
-        const long long row = (z * L.dims[1] + y) * (long long)L.dims[0];
         const bool border = (dz == -r || dz == r || dy == -r || dy == r);
         for (int part = 0; part < 2; ++part) {
           long long xa, xb;
@@ -529,7 +525,8 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, const uint32_t
           else { xa = xb = part ? ix + r : ix - r; }
           xa = max(xa, 0ll); xb = min(xb, (long long)L.dims[0] - 1);
           if (xa > xb) continue;
-          const uint32_t s = __ldg(cell_off + row + xa), e = __ldg(cell_off + row + xb + 1);
+          uint32_t s, e;
+          cell_range(I, (int)z, (int)y, (int)xa, (int)xb, s, e);
           for (uint32_t j = s; j < e; ++j) {
             const P4 p = load_p4(R + j);
             const double d2 = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z);
@@ -667,8 +664,11 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   for (int a = 0; a < 3; ++a) C.ref_maxabs = std::max(C.ref_maxabs, std::max(std::fabs(Rc.bbox_min[a]), std::fabs(Rc.bbox_max[a])));
 
   // the flat kernel packs run lengths into 24 bits and x indices into an fp32 mantissa; otherwise the tile kernel runs
-  const bool use_tile = getenv("ME_NN_TILE") != nullptr || Qc.lat.dims[0] >= (1 << 24) || Rc.lat.dims[0] >= (1 << 24) ||
-                        3 * Rc.max_cell_count >= (1 << 24);
+  const bool any_sparse = Qc.lat.sparse || Rc.lat.sparse;
+  const bool use_tile = !any_sparse && (getenv("ME_NN_TILE") != nullptr || Qc.lat.dims[0] >= (1 << 24) || Rc.lat.dims[0] >= (1 << 24) ||
+                                        3 * Rc.max_cell_count >= (1 << 24));
+  if (any_sparse && 3 * Rc.max_cell_count >= (1 << 24))
+    return fail(ctx, ME_ERR_RANGE, "more than 2^24 / 3 points in one lattice cell of a sparse lattice");
   long long qb, qe, tb = 0, te = 0;
   ME_TRY(query_shard(ctx, qwhich, &qb, &qe));  // flat sweep: contiguous, cell-aligned range of the cell-sorted query order
   if (use_tile) {                              // (before the work buffer is carved up: the tile build scans in it)
@@ -706,6 +706,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     } else {
       FlatGeom G;
       G.qdimx = Qc.lat.dims[0]; G.qdimy = Qc.lat.dims[1];
+      G.q_sparse = Qc.lat.sparse;
       G.rdimx = Rc.lat.dims[0]; G.rdimy = Rc.lat.dims[1]; G.rdimz = Rc.lat.dims[2];
       G.shx = (long long)(Qc.lat.k_lo[0] - Rc.lat.k_lo[0]) * Qc.lat.m;
       G.shy = (long long)(Qc.lat.k_lo[1] - Rc.lat.k_lo[1]) * Qc.lat.m;
@@ -719,11 +720,11 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 32);
       // measured on C3 (profiles/r01_kernel_variants.md): 16-byte table entries, plain walk
       nn_flat_kernel<true, 0><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
-                                                                      Rc.d_cell_off, Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                      index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
                                                                       Qc.d_nn_sq, far_list, far_count);
     }
     ME_LAUNCH_CHECK(ctx);
-    nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, Rc.d_cell_off, Rc.lat, C,
+    nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, index_of(Rc), Rc.lat, C,
                                                                   Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
     ME_LAUNCH_CHECK(ctx);
     if (C.accumulate) {

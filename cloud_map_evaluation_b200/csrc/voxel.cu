@@ -27,7 +27,7 @@ static constexpr int kThreads = 256;
 // out: cnt[nvoxels] (int32), mom[nvoxels * 9] = S1(3), S2(xx,xy,xz,yy,yz,zz) about the voxel centre
 // One HALF-warp per voxel (a voxel is m x m x-runs; with m = 4 that is 16 runs — one per lane of the half-warp).
 __global__ void __launch_bounds__(kThreads)
-voxel_moments_kernel(const P4 *__restrict__ S, const uint32_t *__restrict__ cell_off, Lattice L,
+voxel_moments_kernel(const P4 *__restrict__ S, CellIndex I, Lattice L,
                      int32_t *__restrict__ cnt, double *__restrict__ mom, unsigned long long *__restrict__ n_occupied) {
   const int sub = threadIdx.x & 15;
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 4;
@@ -49,8 +49,8 @@ voxel_moments_kernel(const P4 *__restrict__ S, const uint32_t *__restrict__ cell
                    cz = ((double)(L.k_lo[2] + vz) + 0.5) * L.v;
       for (int t = sub; t < m * m; t += 16) {
         const long long z = (long long)vz * m + t / m, y = (long long)vy * m + t % m;
-        const long long row = (z * L.dims[1] + y) * (long long)L.dims[0] + (long long)vx * m;
-        const uint32_t b = __ldg(cell_off + row), e = __ldg(cell_off + row + m);
+        uint32_t b, e;
+        cell_range(I, (int)z, (int)y, vx * m, vx * m + m - 1, b, e);
         for (uint32_t j = b; j < e; ++j) {
           const P4 p = load_p4(S + j);
           const double dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
@@ -366,7 +366,8 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
   ME_TRY(build_both(ctx));
   Cloud &E = ctx->cloud[ME_CLOUD_EST], &G = ctx->cloud[ME_CLOUD_GT];
   const Lattice Le = E.lat, Lg = G.lat;
-  if (Le.nvoxels >= 0xffffffffll) return fail(ctx, ME_ERR_RANGE, "too many voxels");
+  if (Le.nvoxels < 0 || Lg.nvoxels < 0 || Le.nvoxels >= 0x7fffffffll || Lg.nvoxels >= 0x7fffffffll)
+    return fail(ctx, ME_ERR_RANGE, "vmd_voxel_size is too small for the extent of the clouds: the voxel tables are dense (2^31 voxels at most)");
 
   // work layout: cnt_e | cnt_g | mom_e | mom_g | w_vox | pair_list | rows27
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -395,10 +396,10 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
   {
     StageTimer timer(ctx, 6);
     int blocks_e = (int)std::min<long long>((Le.nvoxels * 16 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
-    voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, E.d_cell_off, Le, cnt_e, mom_e, occ);
+    voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, index_of(E), Le, cnt_e, mom_e, occ);
     ME_LAUNCH_CHECK(ctx);
     int blocks_g = (int)std::min<long long>((Lg.nvoxels * 16 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
-    voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, G.d_cell_off, Lg, cnt_g, mom_g, occ + 1);
+    voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, index_of(G), Lg, cnt_g, mom_g, occ + 1);
     ME_LAUNCH_CHECK(ctx);
   }
   {

@@ -137,6 +137,48 @@ def indoor_scene(n, seed, noise_sigma, start=0, rooms=10):
     return _finish(xyz)
 
 
+def _site_buildings():
+    rng = np.random.RandomState(777)
+    out = []
+    for _ in range(300):
+        cx, cy = rng.uniform(30, 970, 2)
+        ang = rng.uniform(0, np.pi)
+        out.append((cx, cy, ang, rng.uniform(10, 60), rng.uniform(4, 25)))
+    return out
+
+
+def _site_z(x, y):
+    return 12.0 * np.sin(x / 160.0) + 8.0 * np.sin(y / 115.0 + 0.7) + 5.0 * np.sin((x + y) / 47.0) + 0.4 * np.sin(x / 3.1) * np.cos(y / 2.7)
+
+
+def site_scene(n, seed, noise_sigma, start=0):
+    """Site-scale survey (not a BASELINE config; exercises the sparse cell table): a 1 km x 1 km
+    terrain with ~50 m of relief plus 300 building facades, area-uniform sampling."""
+    b = _site_buildings()
+    areas = np.array([1000.0 * 1000.0] + [p[3] * p[4] for p in b])
+    cdf = np.cumsum(areas) / areas.sum()
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    sel = np.minimum(np.searchsorted(cdf, uniform24(seed, idx, 3).astype(np.float64), side="right"), len(areas) - 1)
+    u = uniform24(seed, idx, 0).astype(np.float64)
+    v = uniform24(seed, idx, 1).astype(np.float64)
+    # 24-bit uniforms over 1 km are 6e-5 m apart: add a second draw for the low bits
+    u = u + uniform24(seed, idx, 5).astype(np.float64) * 2.0 ** -24
+    v = v + uniform24(seed, idx, 6).astype(np.float64) * 2.0 ** -24
+    par = np.zeros((len(areas), 5))
+    par[1:] = np.array(b)
+    p = par[sel]
+    g = sel == 0
+    t = (u - 0.5) * p[:, 3]
+    x = np.where(g, u * 1000.0, p[:, 0] + t * np.cos(p[:, 2]))
+    y = np.where(g, v * 1000.0, p[:, 1] + t * np.sin(p[:, 2]))
+    z = _site_z(x, y) + np.where(g, 0.0, v * p[:, 4])
+    xyz = np.stack([x, y, z], axis=1)
+    if noise_sigma > 0:
+        for d in range(3):
+            xyz[:, d] += noise_sigma * gaussian(seed, idx, 8 + 2 * d)
+    return _finish(xyz)
+
+
 # ---- the five BASELINE.json configs (SURVEY.md §8d table) ----------------------------------------------------
 CONFIGS = {
     "C1": dict(desc="100k vs 100k uniform box, 0.1 m voxel, AC+CD only", n_est=100_000, n_gt=100_000, kind="box",
@@ -153,6 +195,10 @@ CONFIGS = {
     "C5": dict(desc="200M vs 200M dense indoor", n_est=200_000_000, n_gt=200_000_000, kind="indoor",
                tau=[0.2, 0.1, 0.08, 0.05, 0.01], nn_radius=0.1, vmd_voxel_size=2.0, mme=True, gt_mme=False,
                awd=True),
+    # not a BASELINE config: site-scale extent for the sparse cell table
+    "S1": dict(desc="100M vs 100M site-scale terrain, 1 km x 1 km x 50 m (sparse cell table)", n_est=100_000_000,
+               n_gt=100_000_000, kind="site", tau=[0.5, 0.3, 0.2, 0.1, 0.05], nn_radius=0.5, vmd_voxel_size=3.0, mme=True,
+               gt_mme=False, awd=True),
 }
 EST_NOISE_SIGMA = 0.01
 GT_SURFACE_NOISE_SIGMA = 0.002
@@ -172,6 +218,9 @@ def make_pair(name, scale=1.0):
     elif cfg["kind"] == "outdoor":
         gt = outdoor_scene(n_gt, GT_SEED, GT_SURFACE_NOISE_SIGMA)
         est = outdoor_scene(n_est, EST_SEED, EST_NOISE_SIGMA)
+    elif cfg["kind"] == "site":
+        gt = site_scene(n_gt, GT_SEED, GT_SURFACE_NOISE_SIGMA)
+        est = site_scene(n_est, EST_SEED, EST_NOISE_SIGMA)
     else:
         gt = indoor_scene(n_gt, GT_SEED, GT_SURFACE_NOISE_SIGMA)
         est = indoor_scene(n_est, EST_SEED, EST_NOISE_SIGMA)

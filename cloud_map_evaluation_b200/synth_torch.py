@@ -143,6 +143,30 @@ def indoor_scene(n, seed, noise_sigma, start=0, rooms=10, device="cpu", chunk=1 
     return out
 
 
+def site_scene(n, seed, noise_sigma, start=0, device="cpu", chunk=1 << 24):
+    b = synth._site_buildings()
+    areas = np.array([1000.0 * 1000.0] + [p[3] * p[4] for p in b])
+    cdf = torch.tensor(np.cumsum(areas) / areas.sum(), dtype=torch.float64, device=device)
+    par_np = np.zeros((len(areas), 5))
+    par_np[1:] = np.array(b)
+    par = torch.tensor(par_np, dtype=torch.float64, device=device)
+    out = torch.empty((n, 3), dtype=torch.float64, device=device)
+    for b0, e0, s in _chunks(n, start, chunk):
+        idx = torch.arange(s, s + (e0 - b0), dtype=torch.int64, device=device)
+        sel = torch.searchsorted(cdf, uniform24(seed, idx, 3).to(torch.float64), right=True).clamp_max(len(areas) - 1)
+        u = uniform24(seed, idx, 0).to(torch.float64) + uniform24(seed, idx, 5).to(torch.float64) * 2.0 ** -24
+        v = uniform24(seed, idx, 1).to(torch.float64) + uniform24(seed, idx, 6).to(torch.float64) * 2.0 ** -24
+        p = par[sel]
+        g = sel == 0
+        t = (u - 0.5) * p[:, 3]
+        x = torch.where(g, u * 1000.0, p[:, 0] + t * torch.cos(p[:, 2]))
+        y = torch.where(g, v * 1000.0, p[:, 1] + t * torch.sin(p[:, 2]))
+        z = (12.0 * torch.sin(x / 160.0) + 8.0 * torch.sin(y / 115.0 + 0.7) + 5.0 * torch.sin((x + y) / 47.0)
+             + 0.4 * torch.sin(x / 3.1) * torch.cos(y / 2.7)) + torch.where(g, torch.zeros_like(v), v * p[:, 4])
+        _finish(_add_noise([x, y, z], seed, idx, noise_sigma), out[b0:e0])
+    return out
+
+
 def make_pair(name, scale=1.0, device="cpu"):
     """(est, gt, cfg) as (N, 3) fp64 tensors on `device` — the same clouds as synth.make_pair (see the module note)."""
     cfg = dict(synth.CONFIGS[name])
@@ -157,6 +181,9 @@ def make_pair(name, scale=1.0, device="cpu"):
     elif cfg["kind"] == "outdoor":
         gt = outdoor_scene(n_gt, synth.GT_SEED, synth.GT_SURFACE_NOISE_SIGMA, device=device)
         est = outdoor_scene(n_est, synth.EST_SEED, synth.EST_NOISE_SIGMA, device=device)
+    elif cfg["kind"] == "site":
+        gt = site_scene(n_gt, synth.GT_SEED, synth.GT_SURFACE_NOISE_SIGMA, device=device)
+        est = site_scene(n_est, synth.EST_SEED, synth.EST_NOISE_SIGMA, device=device)
     else:
         gt = indoor_scene(n_gt, synth.GT_SEED, synth.GT_SURFACE_NOISE_SIGMA, device=device)
         est = indoor_scene(n_est, synth.EST_SEED, synth.EST_NOISE_SIGMA, device=device)

@@ -20,7 +20,7 @@ def test_uniform24_bit_identical():
         np.testing.assert_array_equal(a, b)
 
 
-@pytest.mark.parametrize("name,scale", [("C2", 0.02), ("C4", 0.0005), ("C5", 0.0001)])
+@pytest.mark.parametrize("name,scale", [("C2", 0.02), ("C4", 0.0005), ("C5", 0.0001), ("S1", 0.0002)])
 def test_make_pair_matches_numpy(name, scale):
     est, gt, cfg = synth.make_pair(name, scale=scale)
     t_est, t_gt, t_cfg = synth_torch.make_pair(name, scale=scale, device="cpu")
