@@ -281,15 +281,17 @@ def main():
             ctx.set_cloud_device(A.ME_CLOUD_GT, d_gt.data_ptr(), n_gt, keepalive=d_gt)
         # MapEval::process() order (map_eval.cpp:56,76,85): MME, then the NN metrics, then VMD.  With host buffers
         # the GT upload (copy stream) overlaps the est lattice build + MME, which need the est cloud only.
-        mmes = []
+        # the accumulators stay on the device: sweeps -> (N > 1: all-reduce in place over NCCL) -> one fetch per pass
+        ctx.accum_reset()
         if cfg["mme"]:
-            mmes.append(ctx.eval_mme_accum(A.ME_CLOUD_EST, cfg["nn_radius"], 10))
+            ctx.eval_mme_accum_device(A.ME_CLOUD_EST, cfg["nn_radius"], 10)
             if cfg["gt_mme"]:
-                mmes.append(ctx.eval_mme_accum(A.ME_CLOUD_GT, cfg["nn_radius"], 5))
-        nn_e, nn_g = ctx.eval_nn_accum(p)
+                ctx.eval_mme_accum_device(A.ME_CLOUD_GT, cfg["nn_radius"], 5)
+        ctx.eval_nn_accum_device(p)
         awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5) if cfg["awd"] else None
         if world > 1:
-            mdist.allreduce_accumulators(nn_e, nn_g, mmes, device=dev)
+            mdist.allreduce_block(ctx, dev)
+        nn_e, nn_g, mmes = ctx.accum_fetch(want_mme=(bool(cfg["mme"]), bool(cfg["mme"] and cfg["gt_mme"])))
         results["nn"] = ctx.nn_finalize(p, nn_e, nn_g)
         results["mme"] = [ctx.mme_finalize(m, w) for m, w in zip(mmes, (A.ME_CLOUD_EST, A.ME_CLOUD_GT))]
         results["awd"] = awd

@@ -18,6 +18,7 @@ SYMBOLS = (
     "me_set_normals", "me_estimate_normals", "me_get_normals", "me_build_grid", "me_eval_nn_accum", "me_nn_finalize",
     "me_eval_nn", "me_get_nn", "me_eval_mme_accum", "me_mme_finalize", "me_eval_mme", "me_get_entropies",
     "me_eval_awd", "me_awd_from_rows", "me_free", "me_get_stage_times", "me_launch_count",
+    "me_accum_reset", "me_eval_nn_accum_device", "me_eval_mme_accum_device", "me_accum_block", "me_accum_fetch",
 )
 
 _lib = None
@@ -70,6 +71,12 @@ def load():
     L.me_get_entropies.argtypes = [ctx, C.c_int, C.c_void_p]
     L.me_eval_awd.argtypes = [ctx, C.c_double, C.c_int32, C.c_int32, C.POINTER(A.me_awd_result),
                               C.POINTER(C.c_int64), C.POINTER(dp)]
+    L.me_accum_reset.argtypes = [ctx]
+    L.me_eval_nn_accum_device.argtypes = [ctx, C.POINTER(A.me_nn_params)]
+    L.me_eval_mme_accum_device.argtypes = [ctx, C.c_int, C.c_double, C.c_int32]
+    L.me_accum_block.argtypes = [ctx, C.POINTER(dp), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.me_accum_fetch.argtypes = [ctx, C.POINTER(A.me_nn_accum), C.POINTER(A.me_nn_accum), C.POINTER(A.me_mme_accum),
+                                 C.POINTER(A.me_mme_accum)]
     L.me_free.argtypes = [C.c_void_p]
     L.me_free.restype = None
     L.me_get_stage_times.argtypes = [ctx, dp]

@@ -221,6 +221,30 @@ class MapEvalB200:
                                              w.ctypes.data_as(dp), C.byref(out)))
         return out, w
 
+    # -- device-resident accumulators (multi-GPU passes without host round trips) ---------------------------------
+    def accum_reset(self):
+        self._check(self._L.me_accum_reset(self._ctx))
+
+    def eval_nn_accum_device(self, params):
+        self._check(self._L.me_eval_nn_accum_device(self._ctx, C.byref(params)))
+
+    def eval_mme_accum_device(self, which, radius, min_neighbors):
+        self._check(self._L.me_eval_mme_accum_device(self._ctx, which, float(radius), int(min_neighbors)))
+
+    def accum_block(self):
+        """(device pointer, n_sum, n_max) of the fp64 accumulator block"""
+        ptr = C.POINTER(C.c_double)()
+        ns, nm = C.c_int32(0), C.c_int32(0)
+        self._check(self._L.me_accum_block(self._ctx, C.byref(ptr), C.byref(ns), C.byref(nm)))
+        return C.cast(ptr, C.c_void_p).value, ns.value, nm.value
+
+    def accum_fetch(self, want_mme=(True, False)):
+        e, g = A.me_nn_accum(), A.me_nn_accum()
+        mm = [A.me_mme_accum() if w else None for w in want_mme]
+        self._check(self._L.me_accum_fetch(self._ctx, C.byref(e), C.byref(g), C.byref(mm[0]) if mm[0] else None,
+                                           C.byref(mm[1]) if mm[1] else None))
+        return e, g, [m for m in mm if m is not None]
+
     # -- introspection -----------------------------------------------------------------------------------------
     def stage_times_ms(self):
         ms = (C.c_double * A.ME_N_STAGE_TIMES)()

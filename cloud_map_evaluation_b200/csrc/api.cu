@@ -123,6 +123,7 @@ int me_create(const me_options *opt, me_ctx **out) {
     ctx->own_stream = true;
   }
   bool ok = cudaMalloc(&ctx->d_scratch, kScratchBytes) == cudaSuccess && cudaMallocHost(&ctx->h_pinned, kScratchBytes) == cudaSuccess;
+  ok = ok && cudaMalloc((void **)&ctx->d_block, kBlkTotal * sizeof(double)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->compute_mark, cudaEventDisableTiming) == cudaSuccess;
   for (int w = 0; ok && w < 2; ++w) ok = cudaEventCreateWithFlags(&ctx->cloud[w].upload_done, cudaEventDisableTiming) == cudaSuccess;
@@ -143,6 +144,7 @@ void me_destroy(me_ctx *ctx) {
   free_cloud(ctx->cloud[0]);
   free_cloud(ctx->cloud[1]);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_block) cudaFree(ctx->d_block);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->d_work) cudaFree(ctx->d_work);
   if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
@@ -308,6 +310,74 @@ int me_eval_nn_accum(me_ctx *ctx, const me_nn_params *p, me_nn_accum *est_to_gt,
   if (((dirs & 1) && !est_to_gt) || ((dirs & 2) && !gt_to_est)) return fail(ctx, ME_ERR_INVALID, "null accumulator for a requested direction");
   return run_nn(ctx, p, est_to_gt, gt_to_est);
 }
+
+// ---- device-resident accumulators: sweep -> (all-reduce on the device by the caller) -> one fetch per pass ----------------
+__global__ void block_init_kernel(double *blk) {
+  const int t = threadIdx.x;
+  if (t < me::kBlkSumCount) blk[t] = 0.0;
+  else if (t < me::kBlkTotal) blk[t] = -INFINITY;
+}
+
+extern "C" {
+
+int me_accum_reset(me_ctx *ctx) {
+  ME_ENTER(ctx);
+  block_init_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_block);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
+int me_eval_nn_accum_device(me_ctx *ctx, const me_nn_params *p) {
+  ME_ENTER(ctx);
+  if (!p) return fail(ctx, ME_ERR_INVALID, "null params");
+  if (p->cutoff_mode != ME_CUTOFF_SQDIST_LE_R && p->cutoff_mode != ME_CUTOFF_DIST_LT_R) return fail(ctx, ME_ERR_INVALID, "bad cutoff_mode");
+  if (p->pairing != ME_PAIRING_AS_WRITTEN && p->pairing != ME_PAIRING_GEOMETRIC) return fail(ctx, ME_ERR_INVALID, "bad pairing");
+  return run_nn(ctx, p, nullptr, nullptr, true);
+}
+
+int me_eval_mme_accum_device(me_ctx *ctx, int which, double radius, int32_t min_neighbors) {
+  ME_ENTER(ctx);
+  if (which != ME_CLOUD_EST && which != ME_CLOUD_GT) return fail(ctx, ME_ERR_INVALID, "bad arguments");
+  return run_mme(ctx, which, radius, min_neighbors, nullptr, true);
+}
+
+int me_accum_block(me_ctx *ctx, double **device_block, int32_t *n_sum, int32_t *n_max) {
+  ME_ENTER(ctx);
+  if (device_block) *device_block = ctx->d_block;
+  if (n_sum) *n_sum = kBlkSumCount;
+  if (n_max) *n_max = kBlkMaxCount;
+  return ME_OK;
+}
+
+int me_accum_fetch(me_ctx *ctx, me_nn_accum *est_to_gt, me_nn_accum *gt_to_est, me_mme_accum *mme_est, me_mme_accum *mme_gt) {
+  ME_ENTER(ctx);
+  double *h = (double *)((char *)ctx->h_pinned + 3072);
+  ME_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_block, kBlkTotal * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  auto i64 = [](double v) { return (int64_t)std::llround(v); };
+  me_nn_accum *dirs[2] = {est_to_gt, gt_to_est};
+  for (int d = 0; d < 2; ++d) {
+    me_nn_accum *a = dirs[d];
+    if (!a) continue;
+    const double *b = h + d * kBlkNN;
+    a->n_query = i64(b[0]); a->n_corr = i64(b[1]);
+    for (int k = 0; k < 5; ++k) a->n_inlier[k] = i64(b[2 + k]);
+    a->n_ub = i64(b[7]); a->n_far = i64(b[8]);
+    for (int k = 0; k < 5; ++k) { a->sum_d[k] = b[9 + k]; a->sum_d2[k] = b[14 + k]; }
+    a->sum_d_all = b[19]; a->sum_d2_all = b[20]; a->sum_nn_dist = b[21];
+  }
+  me_mme_accum *mm[2] = {mme_est, mme_gt};
+  for (int w = 0; w < 2; ++w) {
+    me_mme_accum *m = mm[w];
+    if (!m) continue;
+    const double *b = h + kBlkMmeSum + 3 * w, *x = h + kBlkMax + 2 * w;
+    m->n_query = i64(b[0]); m->n_valid = i64(b[1]); m->sum_entropy = b[2];
+    m->max_entropy = x[0]; m->min_entropy = -x[1];
+  }
+  return ME_OK;
+}
+
+}  // extern "C"
 
 static void finalize_dir(const me_nn_accum *a, int64_t n_source, me_dir_result *r) {
   std::memset(r, 0, sizeof(*r));

@@ -129,6 +129,7 @@ struct me_ctx {
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;
   void *h_pinned = nullptr;         // pinned host mirror of the scratch
+  double *d_block = nullptr;        // device-resident accumulator block of the *_device calls (ME_BLOCK_* layout, api.cu)
   // large device scratch (scan partials, far list, voxel tables)
   void *d_work = nullptr;
   size_t work_bytes = 0;
@@ -203,9 +204,18 @@ int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n);
 int voxel_downsample(me_ctx *ctx, int which, double voxel_size, int64_t *n_out);
 int radix_sort_pairs(me_ctx *ctx, unsigned long long *keys, uint32_t *vals, unsigned long long *keys_tmp, uint32_t *vals_tmp,
                      long long n, int key_bits, unsigned long long **keys_sorted, uint32_t **vals_sorted);
-int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e);
+int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e, bool to_block = false);
 int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2);
-int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out);
+int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_accum *out, bool to_block = false);
+
+// layout of me_ctx::d_block (fp64): the SUM-reducible part first, then the MAX-reducible part.  Counts ride as fp64 (exact
+// below 2^53, so their sums are exact and order-independent).
+static constexpr int kBlkNN = 22;                    // per direction: n_query n_corr n_inlier[5] n_ub n_far | sum_d[5] sum_d2[5] sum_d_all sum_d2_all sum_nn
+static constexpr int kBlkMmeSum = 2 * kBlkNN;        // per cloud: n_query n_valid sum_entropy
+static constexpr int kBlkSumCount = kBlkMmeSum + 6;  // = 50 SUM values
+static constexpr int kBlkMax = kBlkSumCount;         // per cloud: max_entropy, -min_entropy
+static constexpr int kBlkMaxCount = 4;
+static constexpr int kBlkTotal = kBlkSumCount + kBlkMaxCount;
 int unsort_entropy(me_ctx *ctx, int which, double *h_entropy);
 int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
             double **rows27);

@@ -644,10 +644,22 @@ __global__ void count_marked_kernel(const int32_t *__restrict__ idx, long long n
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// accumulator block of one direction -> the context's fp64 block (me_eval_nn_accum_device): no host round trip
+__global__ void pack_nn_kernel(const AccBlock *__restrict__ a, const unsigned long long *__restrict__ n_eval, long long n_query,
+                               double *__restrict__ blk) {
+  if (threadIdx.x != 0) return;
+  blk[0] = (double)(n_eval ? (long long)*n_eval : n_query);
+  blk[1] = (double)a->n_corr;
+  for (int k = 0; k < 5; ++k) blk[2 + k] = (double)a->n_inl[k];
+  blk[7] = (double)a->n_ub; blk[8] = (double)a->n_far;
+  for (int k = 0; k < 5; ++k) { blk[9 + k] = a->sum_d[k]; blk[14 + k] = a->sum_d2[k]; }
+  blk[19] = a->sum_d_all; blk[20] = a->sum_d2_all; blk[21] = a->sum_nn;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------------------
-static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_accum *out, int stage) {
+static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_accum *out, int stage, bool to_block) {
   Cloud &Qc = ctx->cloud[qwhich];
   Cloud &Rc = ctx->cloud[1 - qwhich];
   StageTimer timer(ctx, stage);
@@ -748,6 +760,13 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     count_marked_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_nn_idx, Qc.n, n_eval);
     ME_LAUNCH_CHECK(ctx);
   }
+  if (to_block) {      // the accumulators stay on the device (all-reduced there, fetched once per pass)
+    pack_nn_kernel<<<1, 32, 0, ctx->stream>>>(acc, (sharded && use_tile) ? n_eval : nullptr, sharded ? qe - qb : Qc.n,
+                                              ctx->d_block + (qwhich == ME_CLOUD_EST ? 0 : kBlkNN));
+    ME_LAUNCH_CHECK(ctx);
+    Qc.nn_valid = true;
+    return ME_OK;
+  }
   AccBlock *h = (AccBlock *)ctx->h_pinned;
   unsigned long long *h_eval = (unsigned long long *)((char *)ctx->h_pinned + 1024);
   ME_CUDA(ctx, cudaMemcpyAsync(h, acc, sizeof(AccBlock), cudaMemcpyDeviceToHost, ctx->stream));
@@ -774,15 +793,15 @@ int build_both(me_ctx *ctx) {
   return fail(ctx, ME_ERR_RANGE, "could not lay both clouds out on a common lattice");
 }
 
-int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e) {
+int run_nn(me_ctx *ctx, const me_nn_params *p, me_nn_accum *e2g, me_nn_accum *g2e, bool to_block) {
   if (ctx->cloud[0].n <= 0 || ctx->cloud[1].n <= 0)
     return fail(ctx, ME_ERR_EMPTY, "both clouds must be set (map_eval.cpp:32-35)");
   ME_TRY(build_both(ctx));
   const int dirs = p->directions ? p->directions : 3;
   if (e2g) std::memset(e2g, 0, sizeof(*e2g));
   if (g2e) std::memset(g2e, 0, sizeof(*g2e));
-  if ((dirs & 1) && e2g) ME_TRY(run_direction(ctx, ME_CLOUD_EST, p, e2g, 2));
-  if ((dirs & 2) && g2e) ME_TRY(run_direction(ctx, ME_CLOUD_GT, p, g2e, 3));
+  if ((dirs & 1) && (e2g || to_block)) ME_TRY(run_direction(ctx, ME_CLOUD_EST, p, e2g, 2, to_block));
+  if ((dirs & 2) && (g2e || to_block)) ME_TRY(run_direction(ctx, ME_CLOUD_GT, p, g2e, 3, to_block));
   return ME_OK;
 }
 

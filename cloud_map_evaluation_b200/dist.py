@@ -71,3 +71,22 @@ def allreduce_accumulators(nn_e, nn_g, mme_list, device=None, group=None):
 def shard_range(n, rank, world):
     """The contiguous range a rank owns — the same rule as libmapeval_b200 (common.cuh shard_range)."""
     return n * rank // world, n * (rank + 1) // world
+
+
+class _DeviceBlock:
+    """zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def allreduce_block(ctx, device, group=None):
+    """All-reduce the context's device-resident accumulator block in place: ONE SUM all-reduce over the sum-reducible
+    values (counts ride as fp64, exact) and one MAX all-reduce over the entropy extrema — NCCL over NVLink / NVSwitch, no
+    host round trip; the caller fetches the block afterwards (MapEvalB200.accum_fetch)."""
+    import torch
+    import torch.distributed as dist
+    ptr, n_sum, n_max = ctx.accum_block()
+    t = torch.as_tensor(_DeviceBlock(ptr, n_sum + n_max), device=device)
+    dist.all_reduce(t[:n_sum], group=group)
+    dist.all_reduce(t[n_sum:], op=dist.ReduceOp.MAX, group=group)

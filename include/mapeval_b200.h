@@ -223,6 +223,20 @@ ME_API int  me_eval_mme(me_ctx *ctx, int which, double radius, int32_t min_neigh
                  double *entropies_host);
 ME_API int  me_get_entropies(me_ctx *ctx, int which, double *entropies_host);
 
+/* Device-resident accumulators, for multi-GPU passes without host round trips: me_accum_reset clears the context's
+ * accumulator block; the *_device calls run the same sweeps as me_eval_nn_accum / me_eval_mme_accum but leave the partial
+ * accumulators in that block (fp64; counts ride as fp64, exact below 2^53); me_accum_block hands out its DEVICE address:
+ * the first *n_sum values are SUM-reducible, the following *n_max values MAX-reducible (entropy maximum and negated
+ * minimum per cloud) — the caller all-reduces them in place (ncclAllReduce / torch.distributed on the context's stream);
+ * me_accum_fetch copies the block back ONCE and fills the accumulator structs (any of them may be NULL), ready for
+ * me_nn_finalize / me_mme_finalize.  Replaces the reductions of map_eval.cpp:1411,1420,1704-1708 across GPUs. */
+ME_API int  me_accum_reset(me_ctx *ctx);
+ME_API int  me_eval_nn_accum_device(me_ctx *ctx, const me_nn_params *p);
+ME_API int  me_eval_mme_accum_device(me_ctx *ctx, int which, double radius, int32_t min_neighbors);
+ME_API int  me_accum_block(me_ctx *ctx, double **device_block, int32_t *n_sum, int32_t *n_max);
+ME_API int  me_accum_fetch(me_ctx *ctx, me_nn_accum *est_to_gt, me_nn_accum *gt_to_est, me_mme_accum *mme_est,
+                           me_mme_accum *mme_gt);
+
 /* replaces: MapEval::calculateVMD (map_eval.cpp:240-390) with VoxelCalculator::buildVoxelMap / computeVoxelEntropy /
  * updateVoxelMap / computeWassersteinDistanceGaussian / getNeighborIndices (voxel_calculator.cpp:7-56,97-172,241-245).
  * rows27 (nullable): library-allocated n_rows x 27 table = the columns of voxel_errors.txt (map_eval.cpp:292-302),

@@ -500,3 +500,29 @@ def test_small_lattice_budget(api, O):
     omme, oent = O.eval_mme(est, cfg["nn_radius"], 10, want_entropies=True)
     assert mme.n_valid == omme.n_valid
     np.testing.assert_allclose(ent, oent, rtol=RTOL_ENT, atol=0)
+
+
+def test_device_resident_accumulators_equal_the_host_path(api, O):
+    """me_eval_*_accum_device + me_accum_fetch (what bench.py and the multi-GPU pass use) = me_eval_*_accum"""
+    est, gt, cfg = synth.make_pair("C2", scale=0.1)
+    p = A.make_nn_params(cfg["tau"], 1.0)
+    with _ctx(api, est, gt, vmd_voxel_size=cfg["vmd_voxel_size"]) as ctx:
+        m_e = ctx.eval_mme_accum(A.ME_CLOUD_EST, cfg["nn_radius"], 10)
+        m_g = ctx.eval_mme_accum(A.ME_CLOUD_GT, cfg["nn_radius"], 5)
+        e, g = ctx.eval_nn_accum(p)
+        ctx.accum_reset()
+        ctx.eval_mme_accum_device(A.ME_CLOUD_EST, cfg["nn_radius"], 10)
+        ctx.eval_mme_accum_device(A.ME_CLOUD_GT, cfg["nn_radius"], 5)
+        ctx.eval_nn_accum_device(p)
+        ptr, n_sum, n_max = ctx.accum_block()
+        assert ptr and n_sum == 50 and n_max == 4
+        e2, g2, (m_e2, m_g2) = ctx.accum_fetch(want_mme=(True, True))
+    for a, b in ((e, e2), (g, g2)):
+        da, db = A.struct_to_dict(a), A.struct_to_dict(b)
+        for k in ("n_query", "n_corr", "n_inlier", "n_ub", "n_far"):
+            assert da[k] == db[k], k
+        for k in ("sum_d", "sum_d2", "sum_d_all", "sum_d2_all", "sum_nn_dist"):
+            np.testing.assert_allclose(da[k], db[k], rtol=1e-12)
+    for a, b in ((m_e, m_e2), (m_g, m_g2)):
+        assert (a.n_query, a.n_valid) == (b.n_query, b.n_valid)
+        np.testing.assert_allclose([a.sum_entropy, a.min_entropy, a.max_entropy], [b.sum_entropy, b.min_entropy, b.max_entropy], rtol=1e-12)
