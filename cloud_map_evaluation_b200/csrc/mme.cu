@@ -618,8 +618,11 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
       C.r2_hi = (float)((C.r2 + band) * (1.0 + 1e-7));
       C.min_neighbors = min_neighbors;
       C.dimx = c.lat.dims[0]; C.dimy = c.lat.dims[1]; C.dimz = c.lat.dims[2];
-      const char *kv = getenv("ME_MME_KERNEL");          // test hook: "flat" = the round-1 run-table walk
-      const bool use_flat = kv && !strcmp(kv, "flat");
+      // default: the run-table walk (4.45 ms on C3); ME_MME_KERNEL=rows selects the warp-synchronous row walk with deferred
+      // accumulation (4.91 ms on C3: half of its issue slots idle while the longest run of a row finishes —
+      // profiles/r02_kernel_variants.md)
+      const char *kv = getenv("ME_MME_KERNEL");
+      const bool use_flat = !(kv && !strcmp(kv, "rows"));
       if (rings <= 3 && !use_flat) {
         if (rings == 1) ME_TRY(launch_rows<1>(ctx, c, qb, qe, C, acc));
         else if (rings == 2) ME_TRY(launch_rows<2>(ctx, c, qb, qe, C, acc));

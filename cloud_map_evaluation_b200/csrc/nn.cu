@@ -490,6 +490,107 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// rows sweep: the same decomposition and the same exactness rules as the flat sweep, with WARP-UNIFORM control flow — the
+// nine lattice rows of the 3x3x3 block are walked one after the other by all 32 lanes together, and inside a row every
+// lane scans its own three-cell run for max-over-lanes(len) steps (REDUX.MAX).  At any time the lanes of a warp read one
+// row of the reference cloud: a window of a few consecutive 128-byte lines instead of up to nine rows at once, no run
+// table in shared memory, no per-lane refill branches.  The near-tie pass re-walks the rows the same way.
+// ---------------------------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(kFlatThreads, 8)
+nn_rows_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
+               const P4 *__restrict__ R, const float4 *__restrict__ rrel, CellIndex Ir,
+               Lattice Lr, FlatGeom G, NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
+               double *__restrict__ nn_sq, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count) {
+  const unsigned FULL = 0xffffffffu;
+  const float h = G.h;
+  const long long stride = (long long)gridDim.x * kFlatThreads;
+  for (long long base = q_begin + blockIdx.x * (long long)kFlatThreads; base < q_end; base += stride) {
+    const long long i = base + threadIdx.x;
+    const bool live = i < q_end;
+    const long long il = live ? i : q_end - 1;
+    const float4 qr = __ldg(qrel + il);
+    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + il) + 3)));
+    const uint32_t cyz = G.q_sparse ? cq : cq / (uint32_t)G.qdimx;
+    // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
+    const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
+                    cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
+    const long long xa = max(cx - 1, 0ll), xb = min(cx + 1, (long long)G.rdimx - 1);
+    const float tq = (float)cx;
+    float b1 = INFINITY, b2 = INFINITY;
+    uint32_t j1 = 0;
+    uint32_t rs[9];
+    int rl[9];
+#pragma unroll
+    for (int row = 0; row < 9; ++row) {
+      const int dz = row / 3 - 1, dy = row % 3 - 1;
+      const long long z = cz + dz, y = cy + dy;
+      uint32_t s = 0, e = 0;
+      if (live && z >= 0 && z < G.rdimz && y >= 0 && y < G.rdimy && xa <= xb) cell_range(Ir, (int)z, (int)y, (int)xa, (int)xb, s, e);
+      rs[row] = s; rl[row] = (int)(e - s);
+    }
+#pragma unroll
+    for (int row = 0; row < 9; ++row) {
+      const int dz = row / 3 - 1, dy = row % 3 - 1;
+      const float cyf = (float)dy * h - qr.y, czf = (float)dz * h - qr.z;
+      const int len = rl[row];
+      const int maxlen = __reduce_max_sync(FULL, len);
+      const float4 *p = rrel + rs[row];
+      float4 c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int k0 = 0; k0 < maxlen; k0 += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (k0 + u < len) c[u] = __ldg(p + k0 + u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float ddx = fmaf(c[u].w - tq, h, c[u].x - qr.x), ddy = c[u].y + cyf, ddz = c[u].z + czf;
+          const float d32 = (k0 + u < len) ? fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) : INFINITY;
+          const bool lt = d32 < b1;
+          b2 = fminf(b2, lt ? b1 : d32);
+          j1 = lt ? rs[row] + (uint32_t)(k0 + u) : j1;
+          b1 = fminf(b1, d32);
+        }
+      }
+    }
+    if (!live) continue;
+    const P4 q = load_p4(Q + i);
+    Best b;
+    b.init();
+    if (b1 < INFINITY) {
+      // every candidate whose true distance is <= that of j1 has d32 <= b1 + 2 E(b1), E(d2) = 2 sqrt(d2) eta + eta^2 + fp32 rounding
+      const float lim = (b1 + 3.0f * (2.f * sqrtf(b1) * G.eta + G.eta * G.eta + 1e-6f * b1)) * 1.0000005f + 1e-30f;
+      if (b2 > lim) {
+        const P4 pw = load_p4(R + j1);
+        b.offer(q, pw.x, pw.y, pw.z, orig_of(pw.idx));
+      } else {
+        // near-tie (or duplicate points): settle it in fp64 with the reference's operation order
+#pragma unroll
+        for (int row = 0; row < 9; ++row) {
+          const int dz = row / 3 - 1, dy = row % 3 - 1;
+          const float cyf = (float)dy * h - qr.y, czf = (float)dz * h - qr.z;
+#pragma unroll 1
+          for (int k = 0; k < rl[row]; ++k) {
+            const uint32_t jj = rs[row] + (uint32_t)k;
+            const float4 cc = __ldg(rrel + jj);
+            const float ddx = fmaf(cc.w - tq, h, cc.x - qr.x), ddy = cc.y + cyf, ddz = cc.z + czf;
+            if (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= lim) {
+              const P4 pw = load_p4(R + jj);
+              b.offer(q, pw.x, pw.y, pw.z, orig_of(pw.idx));
+            }
+          }
+        }
+      }
+    }
+    finish_query(q, (uint32_t)i, cx, cy, cz, Lr, C, b, nn_idx, nn_d2, nn_sq, far_list, far_count,
+                 (double)cx + (double)qr.x * G.inv_h, (double)cy + (double)qr.y * G.inv_h,
+                 (double)cz + (double)qr.z * G.inv_h, 2e-6);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // far queries: one warp per query, Chebyshev rings r = 0, 1, 2, ... until the best beats the block faces
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -730,6 +831,16 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       // per-axis offset error <= 1e-6 h + fp64 rounding of the cell origins (see mme.cu); vector norm <= sqrt(3) times that
       G.eta = (float)(1.7320508 * (1e-6 * Qc.lat.h + 4e-15 * maxabs));
       const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 32);
+      const char *kv = getenv("ME_NN_KERNEL");      // test hook: "rows" = the warp-synchronous row walk, "flat" = run tables
+      if (kv && !strcmp(kv, "rows"))
+        nn_rows_kernel<2><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
+                                                                  index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                  Qc.d_nn_sq, far_list, far_count);
+      else if (kv && !strcmp(kv, "rows1"))
+        nn_rows_kernel<1><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
+                                                                  index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                  Qc.d_nn_sq, far_list, far_count);
+      else
       // measured on C3 (profiles/r01_kernel_variants.md): 16-byte table entries, plain walk
       nn_flat_kernel<true, 0><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
                                                                       index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,

@@ -90,7 +90,7 @@ def test_generalized_icp(api, O, origin):
     np.testing.assert_allclose(T[:3, :3], To[:3, :3], atol=1e-7 if far else 1e-8)
     np.testing.assert_allclose([reg.fitness, reg.inlier_rmse], [fit, rmse], rtol=1e-5 if far else 1e-6)
     np.testing.assert_allclose(aligned, moved, atol=1e-9)       # est := Transform(original, T)
-    assert reg.inlier_rmse < 0.02
+    assert reg.inlier_rmse < 0.03
 
 
 def test_point_to_plane_icp(api, O):

@@ -19,8 +19,8 @@ for st in settings:
     for k in list(os.environ):
         if k.startswith("ME_"): del os.environ[k]
     cell = 0.0
-    for kv in filter(None, st.split(",")):
-        k, v = kv.split("=")
+    for kv in filter(None, st.split(";")):
+        k, v = kv.split("=", 1)
         if k == "CELL": cell = float(v)
         else: os.environ[k] = v
     ctx = api.MapEvalB200(device=0, vmd_voxel_size=cfg["vmd_voxel_size"], nn_cell_size=cell)
