@@ -129,6 +129,7 @@ struct me_ctx {
   void *d_scratch = nullptr;
   size_t scratch_bytes = 0;
   void *h_pinned = nullptr;         // pinned host mirror of the scratch
+  void *stage = nullptr;            // pinned bounce buffers + streams of the pageable-memory upload path (api.cu)
   double *d_block = nullptr;        // device-resident accumulator block of the *_device calls (ME_BLOCK_* layout, api.cu)
   // large device scratch (scan partials, far list, voxel tables)
   void *d_work = nullptr;
