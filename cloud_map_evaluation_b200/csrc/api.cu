@@ -147,7 +147,9 @@ static bool staged_upload(me_ctx *ctx, void *dst, const void *src, size_t bytes)
       for (size_t c = (size_t)t; c < nchunks; c += kStageThreads, ++use) {
         const int b = use & 1;
         const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
-        if (use >= 2 && cudaEventSynchronize(p->done[t][b]) != cudaSuccess) { rc[t] = 1; return; }      // buffer free again?
+        // the bounce buffer is free once the copy that last used it has run (also one queued by an earlier call; an event
+        // never recorded counts as complete)
+        if (cudaEventSynchronize(p->done[t][b]) != cudaSuccess) { rc[t] = 1; return; }
         std::memcpy(p->pinned[t][b], (const char *)src + off, len);
         if (cudaMemcpyAsync((char *)dst + off, p->pinned[t][b], len, cudaMemcpyHostToDevice, p->stream[t]) != cudaSuccess ||
             cudaEventRecord(p->done[t][b], p->stream[t]) != cudaSuccess) { rc[t] = 1; return; }

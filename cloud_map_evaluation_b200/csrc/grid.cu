@@ -319,28 +319,29 @@ int build_tiles(me_ctx *ctx, int which) {
 // of the points inside a cell is not reproducible between ranks (the scatter takes its slots with atomics), the cell
 // boundaries are: with cell-aligned shards every point is evaluated by exactly one rank.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void shard_bounds_kernel(const P4 *__restrict__ sorted, const uint32_t *__restrict__ cell_off, long long n,
+__global__ void shard_bounds_kernel(const P4 *__restrict__ sorted, const float4 *__restrict__ rel, CellIndex I, long long n,
                                     int rank, int world, unsigned long long *__restrict__ out) {
   const int k = threadIdx.x;      // 0: begin, 1: end
   if (k > 1) return;
   const int r = rank + k;
   long long b = n * r / world;
   if (r >= world) b = n;
-  else if (b > 0) b = cell_off[cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(sorted + b) + 3)))];
+  else if (b > 0) {               // first point of the cell that holds point b
+    int ix, iy, iz;
+    cell_from_tag(I, __double_as_longlong(__ldg(reinterpret_cast<const double *>(sorted + b) + 3)), (int)__ldg(rel + b).w, ix, iy, iz);
+    uint32_t s, e;
+    cell_range(I, iz, iy, ix, ix, s, e);
+    b = s;
+  }
   out[k] = (unsigned long long)b;
 }
 
 int query_shard(me_ctx *ctx, int which, long long *b, long long *e) {
   Cloud &c = ctx->cloud[which];
   if (ctx->world == 1) { *b = 0; *e = c.n; return ME_OK; }
-  if (c.lat.sparse) {      // the sparse build sorts stably: every rank holds the same order, no snapping needed
-    *b = c.n * ctx->rank / ctx->world;
-    *e = c.n * (ctx->rank + 1) / ctx->world;
-    return ME_OK;
-  }
   if (!(c.shard_valid && c.shard_rank == ctx->rank && c.shard_world == ctx->world)) {
     unsigned long long *d = (unsigned long long *)ctx->d_scratch + 12, *h = (unsigned long long *)ctx->h_pinned + 12;
-    shard_bounds_kernel<<<1, 32, 0, ctx->stream>>>(c.d_sorted, c.d_cell_off, c.n, ctx->rank, ctx->world, d);
+    shard_bounds_kernel<<<1, 32, 0, ctx->stream>>>(c.d_sorted, c.d_rel, index_of(c), c.n, ctx->rank, ctx->world, d);
     ME_LAUNCH_CHECK(ctx);
     ME_CUDA(ctx, cudaMemcpyAsync(h, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
