@@ -142,3 +142,20 @@ def test_c3_full_size_against_the_oracle_fixture(api, c3, golden_dir):
     for k in ("n_pairs", "n_scs", "n_voxels_est", "n_voxels_gt", "n_active", "n_old", "n_new"):
         assert ga[k] == ref["awd"][k], k
     np.testing.assert_allclose([ga["awd"], ga["scs"]], [ref["awd"]["awd"], ref["awd"]["scs"]], rtol=1e-8)
+
+
+def test_staged_upload_of_pageable_memory_roundtrip(api):
+    """me_set_cloud from plain (pageable) numpy memory above 32 MB goes through the library's staged upload (host threads +
+    pinned bounce buffers); two uploads back to back reuse the buffers.  What comes back must be what went in."""
+    rs = np.random.RandomState(11)
+    a = rs.rand(3_000_001, 3) * 100.0 - 50.0            # 72 MB, an odd point count
+    b = rs.rand(2_500_003, 3) * 10.0
+    with api.MapEvalB200() as ctx:
+        ctx.set_cloud(A.ME_CLOUD_EST, a)
+        ctx.set_cloud(A.ME_CLOUD_GT, b)
+        np.testing.assert_array_equal(ctx.get_cloud(A.ME_CLOUD_EST), a)
+        np.testing.assert_array_equal(ctx.get_cloud(A.ME_CLOUD_GT), b)
+        ctx.set_cloud(A.ME_CLOUD_EST, b)                 # again, other sizes
+        ctx.set_cloud(A.ME_CLOUD_GT, a)
+        np.testing.assert_array_equal(ctx.get_cloud(A.ME_CLOUD_GT), a)
+        np.testing.assert_array_equal(ctx.get_cloud(A.ME_CLOUD_EST), b)
