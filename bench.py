@@ -156,7 +156,8 @@ def run_reference(args):
     dt = float(np.mean(times))
     v = len(est) / dt / 1e6
     # SURVEY §8d mode (1), the reference's own threading (serial 1-NN loops, serial GT MME): on a 1 M-point sample only —
-    # at full size the serial loops alone take minutes
+    # at full size the serial loops alone take minutes.  (At C3 one full-size pass already takes ~8 min on 128 cores, 7 of
+    # them in the serial voxel-map build whose XOR hash — voxel_calculator.hpp:18-22, restated faithfully — collides.)
     s_est, s_gt, s_cfg, s_scale = _cpu_sample(args.config)
     dt_f = _cpu_pass(s_est, s_gt, s_cfg, threads, faithful=True)
     sample = (f"{args.config} at full size ({len(est)} est vs {len(gt)} gt points), full pass, all-cores mode, "
