@@ -496,8 +496,8 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
 // row of the reference cloud: a window of a few consecutive 128-byte lines instead of up to nine rows at once, no run
 // table in shared memory, no per-lane refill branches.  The near-tie pass re-walks the rows the same way.
 // ---------------------------------------------------------------------------------------------------------------
-template <int U>
-__global__ void __launch_bounds__(kFlatThreads, 8)
+template <int U>      // candidates loaded per inner iteration (all U loads are issued before the first test)
+__global__ void __launch_bounds__(kFlatThreads, (U <= 2 ? 8 : (U <= 4 ? 6 : 4)))
 nn_rows_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
                const P4 *__restrict__ R, const float4 *__restrict__ rrel, CellIndex Ir,
                Lattice Lr, FlatGeom G, NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
@@ -832,14 +832,14 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       G.eta = (float)(1.7320508 * (1e-6 * Qc.lat.h + 4e-15 * maxabs));
       const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 32);
       const char *kv = getenv("ME_NN_KERNEL");      // test hook: "rows" = the warp-synchronous row walk, "flat" = run tables
-      if (kv && !strcmp(kv, "rows"))
-        nn_rows_kernel<2><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
-                                                                  index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
-                                                                  Qc.d_nn_sq, far_list, far_count);
-      else if (kv && !strcmp(kv, "rows1"))
-        nn_rows_kernel<1><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
-                                                                  index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
-                                                                  Qc.d_nn_sq, far_list, far_count);
+#define ME_NN_ROWS_LAUNCH(UU)                                                                                           \
+  nn_rows_kernel<UU><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,          \
+                                                             index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,           \
+                                                             Qc.d_nn_sq, far_list, far_count)
+      if (kv && !strcmp(kv, "rows")) ME_NN_ROWS_LAUNCH(2);
+      else if (kv && !strcmp(kv, "rows1")) ME_NN_ROWS_LAUNCH(1);
+      else if (kv && !strcmp(kv, "rows4")) ME_NN_ROWS_LAUNCH(4);
+      else if (kv && !strcmp(kv, "rows8")) ME_NN_ROWS_LAUNCH(8);
       else
       // measured on C3 (profiles/r01_kernel_variants.md): 16-byte table entries, plain walk
       nn_flat_kernel<true, 0><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
