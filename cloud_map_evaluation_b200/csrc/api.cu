@@ -61,6 +61,7 @@ static void free_cloud(Cloud &c) {
   if (c.d_rel) cudaFree(c.d_rel);
   if (c.d_cell_off) cudaFree(c.d_cell_off);
   if (c.d_cell_id) cudaFree(c.d_cell_id);
+  if (c.d_coarse) cudaFree(c.d_coarse);
   if (c.d_hkey) cudaFree(c.d_hkey);
   if (c.d_hval) cudaFree(c.d_hval);
   if (c.d_nn_idx) cudaFree(c.d_nn_idx);

@@ -73,6 +73,10 @@ struct Cloud {
   long long cap_rel = 0;
   uint32_t *d_cell_off = nullptr;   // dense: ncells + 1 CSR offsets into d_sorted: cell c = [off[c], off[c+1]); sparse: nseg * 32 + 1
   long long cap_cells = 0;
+  uint32_t *d_coarse = nullptr;     // point counts of coarse cells (coarse_f^3 lattice cells each): lets far queries skip empty space
+  long long cap_coarse = 0;
+  int coarse_f = 0;                 // 0: no coarse grid (small lattices)
+  int coarse_dims[3] = {0, 0, 0};
   unsigned long long *d_hkey = nullptr;   // sparse lattice: segment hash table (CellIndex)
   uint32_t *d_hval = nullptr;
   long long cap_hash = 0;
@@ -184,6 +188,20 @@ struct StageTimer {
   StageTimer(me_ctx *c, int s) : ctx(c), stage(s) { cudaEventRecord(c->ev[2 * s], c->stream); }
   ~StageTimer() { cudaEventRecord(ctx->ev[2 * stage + 1], ctx->stream); ctx->ev_used[stage] = true; }
 };
+
+// coarse occupancy grid of a lattice (grid.cu build_coarse): cnt[(cz * cd[1] + cy) * cd[0] + cx] points in the block of f^3 cells
+struct CoarseGrid {
+  const uint32_t *cnt;      // nullptr: none
+  int f;
+  int cd[3];
+};
+inline CoarseGrid coarse_of(const Cloud &c) {
+  CoarseGrid g;
+  g.cnt = c.coarse_f > 0 ? c.d_coarse : nullptr;
+  g.f = c.coarse_f;
+  for (int a = 0; a < 3; ++a) g.cd[a] = c.coarse_dims[a];
+  return g;
+}
 
 inline CellIndex index_of(const Cloud &c) {
   CellIndex I;

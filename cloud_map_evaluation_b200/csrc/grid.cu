@@ -686,6 +686,41 @@ static int build_sparse(me_ctx *ctx, Cloud &c, const Lattice &L, long long *occu
   return ME_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// coarse occupancy grid: point counts of blocks of f^3 lattice cells (f a power of two, at most 256 blocks per axis).
+// The ring expansion of the far-query kernel costs O(r^3) cell lookups in empty space; on fine lattices over large extents
+// (est maps that reach beyond the ground truth, outliers) it walks coarse blocks instead and descends only into occupied
+// ones.  Built for lattices with more than 256 cells along some axis.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) coarse_count_kernel(const P4 *__restrict__ sorted, const float4 *__restrict__ rel, long long n,
+                                                                CellIndex I, int shift, int cdx, int cdy, uint32_t *__restrict__ cnt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    cell_from_tag(I, __double_as_longlong(__ldg(reinterpret_cast<const double *>(sorted + i) + 3)), (int)__ldg(rel + i).w, ix, iy, iz);
+    atomicAdd(cnt + ((long long)(iz >> shift) * cdy + (iy >> shift)) * cdx + (ix >> shift), 1u);
+  }
+}
+
+static int build_coarse(me_ctx *ctx, Cloud &c) {
+  const Lattice &L = c.lat;
+  c.coarse_f = 0;
+  const int dmax = std::max(L.dims[0], std::max(L.dims[1], L.dims[2]));
+  if (dmax <= 256) return ME_OK;
+  int shift = 2;
+  while (((dmax + (1 << shift) - 1) >> shift) > 256) ++shift;
+  const int f = 1 << shift;
+  long long ncoarse = 1;
+  for (int a = 0; a < 3; ++a) { c.coarse_dims[a] = (L.dims[a] + f - 1) >> shift; ncoarse *= c.coarse_dims[a]; }
+  ME_TRY(ensure(ctx, (void **)&c.d_coarse, &c.cap_coarse, ncoarse, sizeof(uint32_t)));
+  ME_CUDA(ctx, cudaMemsetAsync(c.d_coarse, 0, (size_t)ncoarse * sizeof(uint32_t), ctx->stream));
+  const int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  coarse_count_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.d_rel, c.n, index_of(c), shift, c.coarse_dims[0],
+                                                          c.coarse_dims[1], c.d_coarse);
+  ME_LAUNCH_CHECK(ctx);
+  c.coarse_f = f;
+  return ME_OK;
+}
+
 // solo_h > 0: lay the cloud out on a lattice of its own with cells of (about) that edge — used by the MME sweep when the
 // search radius spans many cells of the shared lattice (mme.cu).  A solo lattice is not voxel-aligned and not shared with
 // the other cloud; the next ordinary build_grid() replaces it.
@@ -805,6 +840,7 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     c.max_cell_count = (long long)h_nt[2];
   }
+  ME_TRY(build_coarse(ctx, c));
   c.tiles_valid = false;
   c.shard_valid = false;
   c.grid_valid = true;

@@ -724,15 +724,26 @@ nn_rows_tma_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, lo
 // ---------------------------------------------------------------------------------------------------------------
 // far queries: one warp per query, Chebyshev rings r = 0, 1, 2, ... until the best beats the block faces
 // ---------------------------------------------------------------------------------------------------------------
+// distance (in cells) from continuous coordinate u to the faces of the cell block [a, b] on one axis; faces at or beyond the
+// lattice border are at infinity (nothing lives there)
+__device__ __forceinline__ double block_face_cells(double u, long long a, long long b, int dim) {
+  const double lo = (a <= 0) ? INFINITY : u - (double)a;
+  const double hi = (b + 1 >= dim) ? INFINITY : (double)(b + 1) - u;
+  return fmin(lo, hi);
+}
+
 __global__ void __launch_bounds__(kThreads)
-nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, Lattice L,
+nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, Lattice L, CoarseGrid CG,
               NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
               const uint32_t *__restrict__ far_list, const unsigned int *__restrict__ far_count,
               AccBlock *__restrict__ acc) {
+  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const unsigned int nfar = *far_count;
+  // with a coarse grid the cell-by-cell rings stop after kFineRings and blocks of f^3 cells take over
+  const int fine_rings = CG.cnt ? 4 : 0x7fffffff;
   for (long long w = warp; w < nfar; w += nwarps) {
     const long long i = far_list[w];
     const P4 q = load_p4(Q + i);
@@ -742,8 +753,25 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, L
     const double slack = 1e-9 * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
     double best = nn_d2[i];
     int bidx = nn_idx[i] >= 0 ? nn_idx[i] : 0x7fffffff;
-    bool beyond = false;
-    for (int r = 0;; ++r) {
+    bool beyond = false, done = false;
+    auto warp_argmin = [&]() {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(FULL, best, o);
+        const int oi = __shfl_xor_sync(FULL, bidx, o);
+        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      }
+    };
+    // after a searched block whose faces are g cells away: resolved?  (sets done / beyond)
+    auto settle = [&](double g_cells) {
+      const double g = g_cells * L.h;
+      const double ge = g - slack;
+      const double ge2 = ge > 0 ? ge * ge : 0.0;
+      if (best < ge2) { done = true; return; }
+      if (ge2 > C.max_d2) { beyond = best > C.max_d2; done = true; return; }
+      if (g == INFINITY) done = true;      // the block covers the whole lattice
+    };
+    for (int r = 0; r <= fine_rings && !done; ++r) {
       const int side = 2 * r + 1;
       // rows of the shell: every (dy,dz) in [-r,r]^2; border rows scan the full x range, inner rows two end cells
       for (int t = lane; t < side * side; t += 32) {
@@ -767,20 +795,62 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, L
           }
         }
       }
-      // warp arg-min (distance, then smaller index)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      warp_argmin();
+      settle(fmin(fmin(block_face_cells(ux, ix - r, ix + r, L.dims[0]), block_face_cells(uy, iy - r, iy + r, L.dims[1])),
+                  block_face_cells(uz, iz - r, iz + r, L.dims[2])));
+    }
+    if (!done) {
+      // coarse phase: Chebyshev rings of blocks of f^3 cells around the query's block; empty blocks cost one count load,
+      // occupied blocks that can still hold a closer point are scanned by the whole warp (lanes over the block's f^2 rows)
+      const int f = CG.f;
+      const long long cqx = min(max(ix, 0ll), (long long)L.dims[0] - 1) / f, cqy = min(max(iy, 0ll), (long long)L.dims[1] - 1) / f,
+                      cqz = min(max(iz, 0ll), (long long)L.dims[2] - 1) / f;
+      for (int rc = 0; !done; ++rc) {
+        const int side = 2 * rc + 1;
+        for (int t0 = 0; t0 < side * side; t0 += 32) {
+          const int t = t0 + lane;
+          const bool tv = t < side * side;
+          const int dz = tv ? t / side - rc : 0, dy = tv ? t % side - rc : 0;
+          const long long bz = cqz + dz, by = cqy + dy;
+          const bool row_ok = tv && bz >= 0 && bz < CG.cd[2] && by >= 0 && by < CG.cd[1];
+          const bool border = (dz == -rc || dz == rc || dy == -rc || dy == rc);
+          for (int dxi = 0; dxi < side; ++dxi) {
+            const long long bx = cqx + dxi - rc;
+            bool occ = row_ok && (border || dxi == 0 || dxi == side - 1) && bx >= 0 && bx < CG.cd[0];
+            if (occ) occ = __ldg(CG.cnt + (bz * CG.cd[1] + by) * (long long)CG.cd[0] + bx) != 0;
+            if (occ) {      // can the block hold a point closer than the best so far?
+              const double ex = fmax(0.0, fmax((double)(bx * f) - ux, ux - (double)((bx + 1) * f)));
+              const double ey = fmax(0.0, fmax((double)(by * f) - uy, uy - (double)((by + 1) * f)));
+              const double ez = fmax(0.0, fmax((double)(bz * f) - uz, uz - (double)((bz + 1) * f)));
+              const double lb = sqrt(ex * ex + ey * ey + ez * ez) * L.h - slack;
+              occ = !(lb > 0 && lb * lb > best);
+            }
+            unsigned mask = __ballot_sync(FULL, occ);
+            while (mask) {
+              const int src = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const long long sbx = __shfl_sync(FULL, bx, src), sby = __shfl_sync(FULL, by, src), sbz = __shfl_sync(FULL, bz, src);
+              const int xa = (int)(sbx * f), xb = (int)min(sbx * f + f - 1, (long long)L.dims[0] - 1);
+              for (int row = lane; row < f * f; row += 32) {
+                const long long z = sbz * f + row / f, y = sby * f + row % f;
+                if (z >= L.dims[2] || y >= L.dims[1]) continue;
+                uint32_t s, e;
+                cell_range(I, (int)z, (int)y, xa, xb, s, e);
+                for (uint32_t j = s; j < e; ++j) {
+                  const P4 p = load_p4(R + j);
+                  const double d2 = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z);
+                  const int pi = orig_of(p.idx);
+                  if (d2 < best || (d2 == best && pi < bidx)) { best = d2; bidx = pi; }
+                }
+              }
+              warp_argmin();
+            }
+          }
+        }
+        settle(fmin(fmin(block_face_cells(ux, (cqx - rc) * f, (cqx + rc) * f + f - 1, L.dims[0]),
+                         block_face_cells(uy, (cqy - rc) * f, (cqy + rc) * f + f - 1, L.dims[1])),
+                    block_face_cells(uz, (cqz - rc) * f, (cqz + rc) * f + f - 1, L.dims[2])));
       }
-      const double g = fmin(fmin(face_dist_cells(ux, ix, r, L.dims[0]), face_dist_cells(uy, iy, r, L.dims[1])),
-                            face_dist_cells(uz, iz, r, L.dims[2])) * L.h;
-      const double ge = g - slack;
-      const double ge2 = ge > 0 ? ge * ge : 0.0;
-      if (best < ge2) break;
-      if (ge2 > C.max_d2) { beyond = best > C.max_d2; break; }
-      if (g == INFINITY) break;   // the block covers the whole lattice
     }
     if (lane == 0) {
       atomicAdd(&acc->n_far, 1ull);
@@ -992,7 +1062,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
                                                                       Qc.d_nn_sq, far_list, far_count);
     }
     ME_LAUNCH_CHECK(ctx);
-    nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, index_of(Rc), Rc.lat, C,
+    nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, index_of(Rc), Rc.lat, coarse_of(Rc), C,
                                                                   Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
     ME_LAUNCH_CHECK(ctx);
     if (C.accumulate) {
