@@ -501,12 +501,17 @@ double density_edge(const Cloud &c) {
 }
 
 // (v, m) for a target cell edge, fitting `c` (and `other`, if its bbox is known) into the budget
+static constexpr int kMaxCellsPerVoxelEdge = 512;
+
 static bool pick_spec(const Cloud &c, const Cloud *other, double v_req, double h_target, long long budget, double *v,
                       int *m, Lattice *out, bool allow_sparse) {
   Lattice tmp;
   if (v_req > 0) {
+    // cells per voxel edge: at most kMaxCellsPerVoxelEdge — the voxel stage walks the m x m lattice rows of every voxel, and
+    // degenerate data (duplicates, collinear points) would otherwise drive the cell edge towards zero once the sparse table
+    // lifts the budget
     int mm = (int)std::max(1.0, std::floor(v_req / h_target + 0.5));
-    mm = std::min(mm, 1 << 20);
+    mm = std::min(mm, kMaxCellsPerVoxelEdge);
     for (; mm >= 1; --mm) {
       if (make_lattice(c, v_req, mm, budget, out, allow_sparse) && (!other || make_lattice(*other, v_req, mm, budget, &tmp, allow_sparse))) {
         *v = v_req; *m = mm;
