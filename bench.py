@@ -243,7 +243,7 @@ def main():
     do_e2e = not args.no_e2e
     m_est, m_gt = -(-n_est // world), -(-n_gt // world)          # slice lengths (last slice padded)
     h_est = h_gt = p_est = p_gt = None
-    g_est = g_gt = None
+    g_est = g_gt = s_est = s_gt = None
     if do_e2e:
         def host_slice(d_full, m):
             lo, hi = rank * m, min(d_full.shape[0], (rank + 1) * m)
@@ -259,6 +259,8 @@ def main():
             h_est, h_gt = _alloc_pinned(host_slice(d_est, m_est)), _alloc_pinned(host_slice(d_gt, m_gt))
             g_est = torch.empty((world * m_est, 3), dtype=torch.float64, device=dev)
             g_gt = torch.empty((world * m_gt, 3), dtype=torch.float64, device=dev)
+            s_est = torch.empty((m_est, 3), dtype=torch.float64, device=dev)      # this rank's slice on the device
+            s_gt = torch.empty((m_gt, 3), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
     ctx = api.MapEvalB200(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream,
                           vmd_voxel_size=cfg["vmd_voxel_size"] if cfg["awd"] else 0.0)
@@ -273,9 +275,9 @@ def main():
             ctx.set_cloud(A.ME_CLOUD_EST, p_est)
             ctx.set_cloud(A.ME_CLOUD_GT, p_gt)
         elif mode == "pinned":
-            for h, g, m, n, which in ((h_est, g_est, m_est, n_est, A.ME_CLOUD_EST), (h_gt, g_gt, m_gt, n_gt, A.ME_CLOUD_GT)):
-                g[rank * m:(rank + 1) * m].copy_(h, non_blocking=True)
-                dist.all_gather_into_tensor(g.view(-1), g[rank * m:(rank + 1) * m].view(-1))
+            for h, sl, g, n, which in ((h_est, s_est, g_est, n_est, A.ME_CLOUD_EST), (h_gt, s_gt, g_gt, n_gt, A.ME_CLOUD_GT)):
+                sl.copy_(h, non_blocking=True)                                   # 1/N of the cloud over this rank's PCIe link
+                dist.all_gather_into_tensor(g.view(-1), sl.view(-1))             # the rest over NVLink
                 ctx.set_cloud_device(which, g.data_ptr(), n, keepalive=g)
         else:
             ctx.set_cloud_device(A.ME_CLOUD_EST, d_est.data_ptr(), n_est, keepalive=d_est)
