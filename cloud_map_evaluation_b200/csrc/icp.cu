@@ -259,7 +259,7 @@ __device__ void fast_eigen3x3_normal(const double cov[9], double nrm[3]) {
 static constexpr int kKnnThreads = 128;
 
 __global__ void __launch_bounds__(kKnnThreads)
-knn_normals_kernel(const P4 *__restrict__ S, long long n, CellIndex I, Lattice L, int k, double slack,
+knn_normals_kernel(const P4 *__restrict__ S, long long n, CellIndex I, Lattice L, CoarseGrid CG, int k, double slack,
                    int gicp, double *__restrict__ normals) {
   extern __shared__ __align__(16) unsigned char knn_smem[];
   double *dk = reinterpret_cast<double *>(knn_smem) + threadIdx.x;                                     // dk[t * kKnnThreads]
@@ -273,7 +273,28 @@ knn_normals_kernel(const P4 *__restrict__ S, long long n, CellIndex I, Lattice L
     const long long ix = cix, iy = ciy, iz = ciz;
     int cnt = 0;
     double kth = INFINITY;
-    for (int r = 0;; ++r) {
+    // one candidate: keep the k best (d2, position) pairs sorted; ties go to the smaller caller index
+    auto offer = [&](uint32_t j) {
+      const P4 p = load_p4(S + j);
+      const double d2 = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z);
+      if (cnt == k) {
+        if (d2 > kth) return;
+        if (d2 == kth && orig_of(p.idx) > orig_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + ik[(k - 1) * kKnnThreads]) + 3)))) return;
+      }
+      int pos = cnt < k ? cnt++ : k - 1;
+      while (pos > 0) {
+        const double dp = dk[(pos - 1) * kKnnThreads];
+        if (dp < d2) break;
+        if (dp == d2 && orig_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + ik[(pos - 1) * kKnnThreads]) + 3))) < orig_of(p.idx)) break;
+        dk[pos * kKnnThreads] = dp; ik[pos * kKnnThreads] = ik[(pos - 1) * kKnnThreads];
+        --pos;
+      }
+      dk[pos * kKnnThreads] = d2; ik[pos * kKnnThreads] = j;
+      if (cnt == k) kth = dk[(k - 1) * kKnnThreads];
+    };
+    bool resolved = false;
+    const int fine_rings = CG.cnt ? 8 : 0x7fffffff;      // isolated points: blocks of f^3 cells take over (empty space is skipped)
+    for (int r = 0; r <= fine_rings; ++r) {
       for (int dz = -r; dz <= r; ++dz) {
         const long long z = iz + dz;
         if (z < 0 || z >= L.dims[2]) continue;
@@ -289,31 +310,57 @@ knn_normals_kernel(const P4 *__restrict__ S, long long n, CellIndex I, Lattice L
             if (xa > xb) continue;
             uint32_t s, e;
             cell_range(I, (int)z, (int)y, (int)xa, (int)xb, s, e);
-            for (uint32_t j = s; j < e; ++j) {
-              const P4 p = load_p4(S + j);
-              const double d2 = d2_kd(q.x, q.y, q.z, p.x, p.y, p.z);
-              if (cnt == k) {
-                if (d2 > kth) continue;
-                if (d2 == kth && orig_of(p.idx) > orig_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + ik[(k - 1) * kKnnThreads]) + 3)))) continue;
-              }
-              int pos = cnt < k ? cnt++ : k - 1;
-              while (pos > 0) {
-                const double dp = dk[(pos - 1) * kKnnThreads];
-                if (dp < d2) break;
-                if (dp == d2 && orig_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + ik[(pos - 1) * kKnnThreads]) + 3))) < orig_of(p.idx)) break;
-                dk[pos * kKnnThreads] = dp; ik[pos * kKnnThreads] = ik[(pos - 1) * kKnnThreads];
-                --pos;
-              }
-              dk[pos * kKnnThreads] = d2; ik[pos * kKnnThreads] = j;
-              if (cnt == k) kth = dk[(k - 1) * kKnnThreads];
-            }
+            for (uint32_t j = s; j < e; ++j) offer(j);
           }
         }
       }
       // everything closer than the border of the searched block [i - r, i + r]^3 has been seen
       const double g = (double)r * L.h - slack;
-      if (cnt == k && g > 0 && kth < g * g) break;
-      if (ix - r <= 0 && ix + r >= L.dims[0] - 1 && iy - r <= 0 && iy + r >= L.dims[1] - 1 && iz - r <= 0 && iz + r >= L.dims[2] - 1) break;
+      if (cnt == k && g > 0 && kth < g * g) { resolved = true; break; }
+      if (ix - r <= 0 && ix + r >= L.dims[0] - 1 && iy - r <= 0 && iy + r >= L.dims[1] - 1 && iz - r <= 0 && iz + r >= L.dims[2] - 1) { resolved = true; break; }
+    }
+    if (!resolved) {
+      // coarse phase, from scratch (the blocks cover the cells of the fine phase again): Chebyshev rings of blocks, empty
+      // blocks cost one count load, blocks that cannot hold a point closer than the k-th best are skipped
+      const int f = CG.f;
+      const long long cqx = ix / f, cqy = iy / f, cqz = iz / f;
+      const double ux = cell_coord_cont(q.x, L, 0), uy = cell_coord_cont(q.y, L, 1), uz = cell_coord_cont(q.z, L, 2);
+      cnt = 0; kth = INFINITY;
+      for (int rc = 0;; ++rc) {
+        for (int dz = -rc; dz <= rc; ++dz) {
+          const long long bz = cqz + dz;
+          if (bz < 0 || bz >= CG.cd[2]) continue;
+          for (int dy = -rc; dy <= rc; ++dy) {
+            const long long by = cqy + dy;
+            if (by < 0 || by >= CG.cd[1]) continue;
+            const bool border = (dz == -rc || dz == rc || dy == -rc || dy == rc);
+            for (int dx = -rc; dx <= rc; dx += (border || rc == 0) ? 1 : 2 * rc) {
+              const long long bx = cqx + dx;
+              if (bx < 0 || bx >= CG.cd[0]) continue;
+              if (__ldg(CG.cnt + (bz * CG.cd[1] + by) * (long long)CG.cd[0] + bx) == 0) continue;
+              if (cnt == k) {
+                const double ex = fmax(0.0, fmax((double)(bx * f) - ux, ux - (double)((bx + 1) * f)));
+                const double ey = fmax(0.0, fmax((double)(by * f) - uy, uy - (double)((by + 1) * f)));
+                const double ez = fmax(0.0, fmax((double)(bz * f) - uz, uz - (double)((bz + 1) * f)));
+                const double lb = sqrt(ex * ex + ey * ey + ez * ez) * L.h - slack;
+                if (lb > 0 && lb * lb > kth) continue;
+              }
+              const int xa = (int)(bx * f), xb = (int)min(bx * f + f - 1, (long long)L.dims[0] - 1);
+              for (int row = 0; row < f * f; ++row) {
+                const long long z = bz * f + row / f, y = by * f + row % f;
+                if (z >= L.dims[2] || y >= L.dims[1]) continue;
+                uint32_t s, e;
+                cell_range(I, (int)z, (int)y, xa, xb, s, e);
+                for (uint32_t j = s; j < e; ++j) offer(j);
+              }
+            }
+          }
+        }
+        // the point lies inside its own block: everything closer than rc blocks has been seen
+        const double g = (double)rc * (double)f * L.h - slack;
+        if (cnt == k && g > 0 && kth < g * g) break;
+        if (cqx - rc <= 0 && cqx + rc >= CG.cd[0] - 1 && cqy - rc <= 0 && cqy + rc >= CG.cd[1] - 1 && cqz - rc <= 0 && cqz + rc >= CG.cd[2] - 1) break;
+      }
     }
     // utility::ComputeCovariance over the neighbours (cumulants about the query point instead of the origin: same
     // covariance, without the cancellation of raw coordinates); fewer than 3 neighbours -> identity
@@ -357,7 +404,7 @@ int estimate_normals(me_ctx *ctx, int which, int knn, int gicp) {
   for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(c.bbox_min[a]), std::fabs(c.bbox_max[a])));
   const double slack = 1e-9 * c.lat.h + 4e-14 * maxabs;
   const int blocks = (int)std::min<long long>((c.n + kKnnThreads - 1) / kKnnThreads, (long long)ctx->sm_count * 32);
-  knn_normals_kernel<<<blocks, kKnnThreads, smem, ctx->stream>>>(c.d_sorted, c.n, index_of(c), c.lat, k, slack, gicp, c.d_normal);
+  knn_normals_kernel<<<blocks, kKnnThreads, smem, ctx->stream>>>(c.d_sorted, c.n, index_of(c), c.lat, coarse_of(c), k, slack, gicp, c.d_normal);
   ME_LAUNCH_CHECK(ctx);
   c.normal_valid = true;
   return ME_OK;

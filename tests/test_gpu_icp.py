@@ -69,6 +69,21 @@ def test_estimate_normals_knn20(api, O):
     assert np.mean(dots > 0) > 0.999
 
 
+def test_estimate_normals_with_isolated_points(api, O):
+    """outliers tens of metres from the scene: their 20 neighbours lie far away (the search walks coarse blocks of cells
+    through the empty space); the lattice over the 100 m extent is sparse"""
+    rs = np.random.RandomState(8)
+    xyz = np.concatenate([_scene(120_000, 6, 0.004), rs.rand(300, 3) * 100.0 - 40.0]).astype(np.float32).astype(np.float64)
+    with api.MapEvalB200() as ctx:
+        ctx.set_cloud(A.ME_CLOUD_EST, xyz)
+        ctx.set_cloud(A.ME_CLOUD_GT, xyz[:100])
+        got = ctx.estimate_normals(A.ME_CLOUD_EST, 20)
+    exp = O.estimate_normals_knn(xyz, 20)
+    dots = np.abs(np.einsum("ni,ni->n", got, exp))
+    assert np.mean(dots > 1 - 1e-6) > 0.9995
+    assert np.mean(dots[-300:] > 1 - 1e-6) > 0.97          # the outliers themselves (near-degenerate neighbourhoods aside)
+
+
 @pytest.mark.parametrize("origin", [(0.0, 0.0, 0.0), (1500.0, -800.0, 40.0)])
 def test_generalized_icp(api, O, origin):
     est, gt = _pair(origin=origin)
