@@ -309,8 +309,11 @@ __device__ __forceinline__ bool seg_find(const CellIndex &I, unsigned long long 
 }
 // points of the cells [xa, xb] of lattice row (y, z): [s, e) of the sorted cloud; the caller keeps 0 <= xa <= xb < dimx
 // and the row inside the lattice
+// SP: -1 = decide at run time (I.sparse), 0 / 1 = compile-time dense / sparse (the hot sweeps are instantiated for both, so
+// the dense path carries no trace of the hash lookup)
+template <int SP = -1>
 __device__ __forceinline__ void cell_range(const CellIndex &I, int z, int y, int xa, int xb, uint32_t &s, uint32_t &e) {
-  if (!I.sparse) {
+  if (SP == 0 || (SP < 0 && !I.sparse)) {
     const uint32_t row = ((uint32_t)z * (uint32_t)I.dimy + (uint32_t)y) * (uint32_t)I.dimx;
     s = __ldg(I.off + row + (uint32_t)xa);
     e = __ldg(I.off + row + (uint32_t)xb + 1);

@@ -242,80 +242,6 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const double *__restr
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// two-pass scatter (ME_BUILD=bucket): the one-pass scatter writes 32-byte records at random over the whole sorted array
-// (~0.8 TB/s of effective write bandwidth).  Pass 1 partitions the records into buckets of consecutive lattice rows
-// (<= kMaxBuckets of them; a CTA reserves one range per bucket for its tile, so a bucket receives runs of records);
-// pass 2 walks the buckets in order and places every record in its cell: its writes fall into a window of a few MB that
-// moves monotonically through the output, i.e. they meet in L2 and leave it as full lines.  The fp32 screening copy is
-// written by pass 2 as well (the separate rel pass goes away).
-// ---------------------------------------------------------------------------------------------------------------
-static constexpr int kMaxBuckets = 1024;
-static constexpr int kBucketItems = 8;      // points per thread and tile
-
-__global__ void bucket_init_kernel(const uint32_t *__restrict__ start /* off + 1: start[c] */, long long ncells, long long cells_per_bucket,
-                                   int nb, uint32_t *__restrict__ cursor) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nb) cursor[b] = start[min((long long)b * cells_per_bucket, ncells - 1)];
-}
-
-__global__ void __launch_bounds__(kThreads) bucket_partition_kernel(const double *__restrict__ xyz, long long n,
-                                                                    const uint32_t *__restrict__ cell_id, long long cells_per_bucket,
-                                                                    int nb, uint32_t *__restrict__ cursor, P4 *__restrict__ inter) {
-  __shared__ uint32_t cnt[kMaxBuckets];
-  const long long ntiles = (n + (long long)kThreads * kBucketItems - 1) / ((long long)kThreads * kBucketItems);
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    for (int k = threadIdx.x; k < nb; k += kThreads) cnt[k] = 0;
-    __syncthreads();
-    uint32_t cell[kBucketItems], local[kBucketItems];
-    int bk[kBucketItems];
-    const long long base = tile * (long long)kThreads * kBucketItems;
-#pragma unroll
-    for (int j = 0; j < kBucketItems; ++j) {
-      const long long i = base + (long long)j * kThreads + threadIdx.x;
-      bk[j] = -1;
-      if (i < n) {
-        cell[j] = __ldg(cell_id + i);
-        bk[j] = (int)((long long)cell[j] / cells_per_bucket);
-        local[j] = atomicAdd(&cnt[bk[j]], 1u);
-      }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < nb; k += kThreads) {
-      const uint32_t c = cnt[k];
-      if (c) cnt[k] = atomicAdd(cursor + k, c);      // the tile's range inside bucket k
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kBucketItems; ++j) {
-      const long long i = base + (long long)j * kThreads + threadIdx.x;
-      if (bk[j] < 0) continue;
-      const double x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
-      double2 *o = reinterpret_cast<double2 *>(inter + (cnt[bk[j]] + local[j]));
-      o[0] = make_double2(x, y);
-      o[1] = make_double2(z, __longlong_as_double((long long)(((unsigned long long)cell[j] << 32) | (unsigned long long)i)));
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(kThreads) bucket_place_kernel(const P4 *__restrict__ inter, long long n, Lattice L,
-                                                                uint32_t *__restrict__ cell_cursor, P4 *__restrict__ sorted,
-                                                                float4 *__restrict__ rel) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const P4 p = load_p4(inter + i);
-    const uint32_t c = cell_of(p.idx);
-    const uint32_t slot = atomicAdd(cell_cursor + c, 1u);
-    double2 *o = reinterpret_cast<double2 *>(sorted + slot);
-    o[0] = make_double2(p.x, p.y);
-    o[1] = make_double2(p.z, __longlong_as_double(p.idx));
-    const uint32_t ix = c % (uint32_t)L.dims[0];
-    const uint32_t cyz = c / (uint32_t)L.dims[0];
-    const uint32_t iy = cyz % (uint32_t)L.dims[1], iz = cyz / (uint32_t)L.dims[1];
-    rel[slot] = make_float4((float)cell_rel(p.x, ix, L, 0), (float)cell_rel(p.y, iy, L, 1), (float)cell_rel(p.z, iz, L, 2), (float)ix);
-  }
-}
-
 // fp32 screening copy of the sorted cloud (streaming pass, coalesced both ways): offset of every point from the origin
 // of its own cell (|offset| < ~h, so the fp32 rounding error is ~3e-8 h whatever the world extent) and the cell's x
 // index.  The sweeps rebuild the offset between two points as (ix_a - ix_b) * h + (rel_a - rel_b).
@@ -818,30 +744,10 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, c.n, sizeof(P4)));
     ME_TRY(ensure(ctx, (void **)&c.d_rel, &c.cap_rel, c.n, sizeof(float4)));
     int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-    const char *bm = getenv("ME_BUILD");
-    if (bm && !strcmp(bm, "bucket") && c.n >= (1 << 20)) {
-      // buckets of consecutive lattice rows, ~n / kMaxBuckets points or more each
-      const long long nrows = (long long)L.dims[1] * L.dims[2];
-      const long long rows_per_bucket = (nrows + kMaxBuckets - 1) / kMaxBuckets;
-      const long long cpb = rows_per_bucket * L.dims[0];
-      const int nb = (int)((L.ncells + cpb - 1) / cpb);
-      ME_TRY(ensure_work(ctx, (size_t)c.n * sizeof(P4) + 4096 + (size_t)kMaxBuckets * sizeof(uint32_t)));
-      uint32_t *bcur = (uint32_t *)ctx->d_work;
-      P4 *inter = (P4 *)((char *)ctx->d_work + 4096);
-      bucket_init_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, cpb, nb, bcur);
-      ME_LAUNCH_CHECK(ctx);
-      const long long ntiles = (c.n + (long long)kThreads * kBucketItems - 1) / ((long long)kThreads * kBucketItems);
-      bucket_partition_kernel<<<(int)std::min<long long>(ntiles, (long long)ctx->sm_count * 8), kThreads, 0, ctx->stream>>>(
-          c.d_xyz, c.n, c.d_cell_id, cpb, nb, bcur, inter);
-      ME_LAUNCH_CHECK(ctx);
-      bucket_place_kernel<<<blocks, kThreads, 0, ctx->stream>>>(inter, c.n, L, c.d_cell_off + 1, c.d_sorted, c.d_rel);
-      ME_LAUNCH_CHECK(ctx);
-    } else {
-      scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
-      ME_LAUNCH_CHECK(ctx);
-      rel_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.n, L, c.d_rel);
-      ME_LAUNCH_CHECK(ctx);
-    }
+    scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
+    ME_LAUNCH_CHECK(ctx);
+    rel_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.n, L, c.d_rel);
+    ME_LAUNCH_CHECK(ctx);
     ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     c.max_cell_count = (long long)h_nt[2];
   }

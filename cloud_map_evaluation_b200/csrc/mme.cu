@@ -192,7 +192,7 @@ __device__ __forceinline__ float gap2(int d, float u) {
   return g > 0.f ? g * g : 0.f;
 }
 
-template <int R, bool E16, int U2>      // U2: 0 plain walk, 1 two candidates (two loads in flight) per iteration
+template <int R, bool E16, int U2, int SP>      // U2: 0 plain walk, 1 two candidates (two loads in flight) per iteration; SP: sparse cell table
 // 8 CTAs/SM at R <= 2 (64 registers, two spilled doubles): 4.62 -> 4.44 ms on C3; at R = 3 the 49-row table bounds it at 4
 __global__ void __launch_bounds__(kFlatThreads, (R <= 2 ? 8 : 4))
 mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long q_begin, long long q_end,
@@ -209,7 +209,7 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
     const float4 qr = __ldg(rel + i);
     const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + i) + 3)));
     const int ix = (int)qr.w;
-    const uint32_t cyz = I.sparse ? cq : cq / (uint32_t)C.dimx;
+    const uint32_t cyz = SP ? cq : cq / (uint32_t)C.dimx;
     const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
     const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
     float gl[R], gr[R];      // squared gaps to the d-th cell on the left / right along x (increasing in d)
@@ -230,7 +230,7 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
         for (int d = 0; d < R; ++d) { da -= (gl[d] <= rem) ? 1 : 0; db += (gr[d] <= rem) ? 1 : 0; }
         const int xa = max(ix + da, 0), xb = min(ix + db, C.dimx - 1);
         uint32_t s = 0, e = 0;
-        if ((unsigned)z < (unsigned)C.dimz && (unsigned)y < (unsigned)C.dimy && rem >= 0.f) cell_range(I, z, y, xa, xb, s, e);
+        if ((unsigned)z < (unsigned)C.dimz && (unsigned)y < (unsigned)C.dimy && rem >= 0.f) cell_range<SP>(I, z, y, xa, xb, s, e);
         if (e > s) { T.put(nrun, tid, s, e, dy + R, dz + R, (float)dy * h - qr.y, czv); ++nrun; }
       }
     }
@@ -538,11 +538,16 @@ static int launch_flat(me_ctx *ctx, Cloud &c, long long qb, long long qe, const 
   constexpr int NROW = (2 * R + 1) * (2 * R + 1);
   const size_t smem = (size_t)NROW * kFlatThreads * RunTab<E16>::kEntryBytes;
   // per launch (function attributes are per device; a process may drive several devices through several contexts)
-  if (smem > 48 * 1024)
-    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) {
+    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ME_CUDA(ctx, cudaFuncSetAttribute(mme_flat_kernel<R, E16, U2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   // fine-grained grid (~2 queries per thread): 64 CTAs/SM -> 4.83 ms, 256 -> 4.62 ms, 1024 -> 4.67 ms
   const int blocks = (int)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 256);
-  mme_flat_kernel<R, E16, U2><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, index_of(c), C, c.d_entropy, acc);
+  if (c.lat.sparse)
+    mme_flat_kernel<R, E16, U2, 1><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, index_of(c), C, c.d_entropy, acc);
+  else
+    mme_flat_kernel<R, E16, U2, 0><<<blocks, kFlatThreads, smem, ctx->stream>>>(c.d_sorted, c.d_rel, qb, qe, index_of(c), C, c.d_entropy, acc);
   ME_LAUNCH_CHECK(ctx);
   return ME_OK;
 }

@@ -496,7 +496,7 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
 // row of the reference cloud: a window of a few consecutive 128-byte lines instead of up to nine rows at once, no run
 // table in shared memory, no per-lane refill branches.  The near-tie pass re-walks the rows the same way.
 // ---------------------------------------------------------------------------------------------------------------
-template <int U>      // candidates loaded per inner iteration (all U loads are issued before the first test)
+template <int U, int SP>      // U candidates loaded per inner iteration (all issued before the first test); SP: sparse reference table
 __global__ void __launch_bounds__(kFlatThreads, (U <= 2 ? 8 : (U <= 4 ? 6 : 4)))
 nn_rows_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
                const P4 *__restrict__ R, const float4 *__restrict__ rrel, CellIndex Ir,
@@ -526,7 +526,7 @@ nn_rows_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
       const int dz = row / 3 - 1, dy = row % 3 - 1;
       const long long z = cz + dz, y = cy + dy;
       uint32_t s = 0, e = 0;
-      if (live && z >= 0 && z < G.rdimz && y >= 0 && y < G.rdimy && xa <= xb) cell_range(Ir, (int)z, (int)y, (int)xa, (int)xb, s, e);
+      if (live && z >= 0 && z < G.rdimz && y >= 0 && y < G.rdimy && xa <= xb) cell_range<SP>(Ir, (int)z, (int)y, (int)xa, (int)xb, s, e);
       rs[row] = s; rl[row] = (int)(e - s);
     }
 #pragma unroll
@@ -587,137 +587,6 @@ nn_rows_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
     finish_query(q, (uint32_t)i, cx, cy, cz, Lr, C, b, nn_idx, nn_d2, nn_sq, far_list, far_count,
                  (double)cx + (double)qr.x * G.inv_h, (double)cy + (double)qr.y * G.inv_h,
                  (double)cz + (double)qr.z * G.inv_h, 2e-6);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// rows sweep with TMA staging (ME_NN_KERNEL=tma).  The 32 queries of a warp are x-neighbours of one lattice row, so for each
-// of the nine (dy, dz) rows their three-cell runs overlap into ONE contiguous range of the reference cloud — [min s, max e),
-// ~37 candidates on C3.  One lane brings all nine ranges into the warp's shared-memory slab with nine cp.async.bulk copies
-// (TMA, SASS UBLKCP; completion on the warp's own mbarrier), all nine in flight at once, and the walk then reads
-// candidates with LDS only: the global-memory latency is paid once per 32 queries instead of once per row and step.
-// A range that does not fit its slot (warps that straddle lattice rows, dense clusters) is walked from global memory.
-// ---------------------------------------------------------------------------------------------------------------
-static constexpr int kTmaCap = 64;                               // candidates per staged row
-static constexpr int kTmaWarpBytes = 9 * kTmaCap * (int)sizeof(float4);
-
-template <int U>
-__global__ void __launch_bounds__(kFlatThreads, 5)
-nn_rows_tma_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long long q_begin, long long q_end,
-                   const P4 *__restrict__ R, const float4 *__restrict__ rrel, CellIndex Ir,
-                   Lattice Lr, FlatGeom G, NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
-                   double *__restrict__ nn_sq, uint32_t *__restrict__ far_list, unsigned int *__restrict__ far_count) {
-  extern __shared__ __align__(128) unsigned char tma_smem[];
-  __shared__ __align__(8) uint64_t wbar[kFlatThreads / 32];
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 *slab = reinterpret_cast<float4 *>(tma_smem + (size_t)warp * kTmaWarpBytes);
-  if (lane == 0) mbar_init(&wbar[warp], 1);
-  __syncwarp();
-  uint32_t phase = 0;
-  const float h = G.h;
-  const long long stride = (long long)gridDim.x * kFlatThreads;
-  for (long long base = q_begin + blockIdx.x * (long long)kFlatThreads; base < q_end; base += stride) {
-    const long long i = base + threadIdx.x;
-    const bool live = i < q_end;
-    const long long il = live ? i : q_end - 1;
-    const float4 qr = __ldg(qrel + il);
-    const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + il) + 3)));
-    const uint32_t cyz = G.q_sparse ? cq : cq / (uint32_t)G.qdimx;
-    const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
-                    cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
-    const long long xa = max(cx - 1, 0ll), xb = min(cx + 1, (long long)G.rdimx - 1);
-    const float tq = (float)cx;
-    uint32_t rs[9], S[9], H[9];
-    int rl[9];
-    bool staged[9];
-    uint32_t tx_bytes = 0;
-#pragma unroll
-    for (int row = 0; row < 9; ++row) {
-      const int dz = row / 3 - 1, dy = row % 3 - 1;
-      const long long z = cz + dz, y = cy + dy;
-      uint32_t s = 0, e = 0;
-      if (live && z >= 0 && z < G.rdimz && y >= 0 && y < G.rdimy && xa <= xb) cell_range(Ir, (int)z, (int)y, (int)xa, (int)xb, s, e);
-      rs[row] = s; rl[row] = (int)(e - s);
-      // the union of the lanes' runs of this row (warp-uniform values)
-      S[row] = __reduce_min_sync(FULL, e > s ? s : 0xffffffffu);
-      H[row] = __reduce_max_sync(FULL, e > s ? e : 0u);
-      staged[row] = H[row] > S[row] && H[row] - S[row] <= (uint32_t)kTmaCap;
-      if (staged[row]) tx_bytes += (H[row] - S[row]) * (uint32_t)sizeof(float4);
-    }
-    // every lane is done with the previous batch's slab (__syncwarp at the end of the loop body): bring the ranges in
-    if (tx_bytes && lane == 0) {
-      mbar_expect_tx(&wbar[warp], tx_bytes);
-#pragma unroll
-      for (int row = 0; row < 9; ++row)
-        if (staged[row])
-          tma_bulk_g2s(slab + row * kTmaCap, rrel + S[row], (H[row] - S[row]) * (uint32_t)sizeof(float4), &wbar[warp]);
-    }
-    if (tx_bytes) { mbar_wait(&wbar[warp], phase); phase ^= 1u; }
-
-    float b1 = INFINITY, b2 = INFINITY;
-    uint32_t j1 = 0;
-#pragma unroll
-    for (int row = 0; row < 9; ++row) {
-      const int dz = row / 3 - 1, dy = row % 3 - 1;
-      const float cyf = (float)dy * h - qr.y, czf = (float)dz * h - qr.z;
-      const int len = rl[row];
-      const int maxlen = __reduce_max_sync(FULL, len);
-      const float4 *pg = rrel + rs[row];
-      const float4 *ps = slab + row * kTmaCap + (rs[row] - S[row]);
-      const bool st = staged[row];
-      float4 c[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-      for (int k0 = 0; k0 < maxlen; k0 += U) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (k0 + u < len) c[u] = st ? ps[k0 + u] : __ldg(pg + k0 + u);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float ddx = fmaf(c[u].w - tq, h, c[u].x - qr.x), ddy = c[u].y + cyf, ddz = c[u].z + czf;
-          const float d32 = (k0 + u < len) ? fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) : INFINITY;
-          const bool lt = d32 < b1;
-          b2 = fminf(b2, lt ? b1 : d32);
-          j1 = lt ? rs[row] + (uint32_t)(k0 + u) : j1;
-          b1 = fminf(b1, d32);
-        }
-      }
-    }
-    if (live) {
-      const P4 q = load_p4(Q + i);
-      Best b;
-      b.init();
-      if (b1 < INFINITY) {
-        const float lim = (b1 + 3.0f * (2.f * sqrtf(b1) * G.eta + G.eta * G.eta + 1e-6f * b1)) * 1.0000005f + 1e-30f;
-        if (b2 > lim) {
-          const P4 pw = load_p4(R + j1);
-          b.offer(q, pw.x, pw.y, pw.z, orig_of(pw.idx));
-        } else {
-          // near-tie (or duplicate points): settle it in fp64 with the reference's operation order
-#pragma unroll
-          for (int row = 0; row < 9; ++row) {
-            const int dz = row / 3 - 1, dy = row % 3 - 1;
-            const float cyf = (float)dy * h - qr.y, czf = (float)dz * h - qr.z;
-#pragma unroll 1
-            for (int k = 0; k < rl[row]; ++k) {
-              const uint32_t jj = rs[row] + (uint32_t)k;
-              const float4 cc = __ldg(rrel + jj);
-              const float ddx = fmaf(cc.w - tq, h, cc.x - qr.x), ddy = cc.y + cyf, ddz = cc.z + czf;
-              if (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= lim) {
-                const P4 pw = load_p4(R + jj);
-                b.offer(q, pw.x, pw.y, pw.z, orig_of(pw.idx));
-              }
-            }
-          }
-        }
-      }
-      finish_query(q, (uint32_t)i, cx, cy, cz, Lr, C, b, nn_idx, nn_d2, nn_sq, far_list, far_count,
-                   (double)cx + (double)qr.x * G.inv_h, (double)cy + (double)qr.y * G.inv_h,
-                   (double)cz + (double)qr.z * G.inv_h, 2e-6);
-    }
-    __syncwarp();      // the slab is free for the next batch
   }
 }
 
@@ -1032,34 +901,21 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       // per-axis offset error <= 1e-6 h + fp64 rounding of the cell origins (see mme.cu); vector norm <= sqrt(3) times that
       G.eta = (float)(1.7320508 * (1e-6 * Qc.lat.h + 4e-15 * maxabs));
       const unsigned grid = (unsigned)std::min<long long>((qe - qb + kFlatThreads - 1) / kFlatThreads, (long long)ctx->sm_count * 32);
-      const char *kv = getenv("ME_NN_KERNEL");      // test hook: "rows" = the warp-synchronous row walk, "flat" = run tables
-#define ME_NN_ROWS_LAUNCH(UU)                                                                                           \
-  nn_rows_kernel<UU><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,          \
-                                                             index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,           \
-                                                             Qc.d_nn_sq, far_list, far_count)
-      if (kv && !strcmp(kv, "rows")) ME_NN_ROWS_LAUNCH(2);
-      else if (kv && !strcmp(kv, "rows1")) ME_NN_ROWS_LAUNCH(1);
-      else if (kv && !strcmp(kv, "rows4")) ME_NN_ROWS_LAUNCH(4);
-      else if (kv && !strcmp(kv, "rows8")) ME_NN_ROWS_LAUNCH(8);
-      else if (kv && (!strcmp(kv, "tma") || !strcmp(kv, "tma4"))) {
-        const size_t smem = (size_t)(kFlatThreads / 32) * kTmaWarpBytes;
-        if (!strcmp(kv, "tma")) {
-          ME_CUDA(ctx, cudaFuncSetAttribute(nn_rows_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          nn_rows_tma_kernel<2><<<grid, kFlatThreads, smem, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
-                                                                         index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
-                                                                         Qc.d_nn_sq, far_list, far_count);
-        } else {
-          ME_CUDA(ctx, cudaFuncSetAttribute(nn_rows_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          nn_rows_tma_kernel<4><<<grid, kFlatThreads, smem, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
-                                                                         index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
-                                                                         Qc.d_nn_sq, far_list, far_count);
-        }
-      }
+      // default: the warp-synchronous row walk, 4 candidates per iteration (1.17 / 1.56 ms on C3 against 1.41 / 1.79 ms for the
+      // run-table walk, which stays behind ME_NN_KERNEL=flat; profiles/r02_kernel_variants.md)
+      const char *kv = getenv("ME_NN_KERNEL");
+      if (kv && !strcmp(kv, "flat"))
+        nn_flat_kernel<true, 0><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
+                                                                        index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                        Qc.d_nn_sq, far_list, far_count);
+      else if (Rc.lat.sparse)
+        nn_rows_kernel<4, 1><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
+                                                                     index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                     Qc.d_nn_sq, far_list, far_count);
       else
-      // measured on C3 (profiles/r01_kernel_variants.md): 16-byte table entries, plain walk
-      nn_flat_kernel<true, 0><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
-                                                                      index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
-                                                                      Qc.d_nn_sq, far_list, far_count);
+        nn_rows_kernel<4, 0><<<grid, kFlatThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.d_rel, qb, qe, Rc.d_sorted, Rc.d_rel,
+                                                                     index_of(Rc), Rc.lat, G, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                     Qc.d_nn_sq, far_list, far_count);
     }
     ME_LAUNCH_CHECK(ctx);
     nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, index_of(Rc), Rc.lat, coarse_of(Rc), C,

@@ -26,8 +26,20 @@ static constexpr int kThreads = 256;
 // ---- per-voxel moments -----------------------------------------------------------------------------------------
 // out: cnt[nvoxels] (int32), mom[nvoxels * 9] = S1(3), S2(xx,xy,xz,yy,yz,zz) about the voxel centre
 // One HALF-warp per voxel (a voxel is m x m x-runs; with m = 4 that is 16 runs — one per lane of the half-warp).
+// sparse lattices: the voxel grid of a site-scale scene is mostly empty, and probing the m x m rows of an empty voxel costs
+// hash lookups — count the points per voxel from the sorted cloud first, the moments kernel then skips empty voxels
 __global__ void __launch_bounds__(kThreads)
-voxel_moments_kernel(const P4 *__restrict__ S, CellIndex I, Lattice L,
+voxel_precount_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long long n, CellIndex I, Lattice L,
+                      int32_t *__restrict__ cnt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    cell_from_tag(I, __double_as_longlong(__ldg(reinterpret_cast<const double *>(S + i) + 3)), (int)__ldg(rel + i).w, ix, iy, iz);
+    atomicAdd(cnt + ((long long)(iz / L.m) * L.nvox[1] + iy / L.m) * L.nvox[0] + ix / L.m, 1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+voxel_moments_kernel(const P4 *__restrict__ S, CellIndex I, Lattice L, int precounted,
                      int32_t *__restrict__ cnt, double *__restrict__ mom, unsigned long long *__restrict__ n_occupied) {
   const int sub = threadIdx.x & 15;
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 4;
@@ -41,7 +53,7 @@ voxel_moments_kernel(const P4 *__restrict__ S, CellIndex I, Lattice L,
     const bool live = vox < L.nvoxels;
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int n = 0;
-    if (live) {
+    if (live && !(precounted && cnt[vox] == 0)) {
       const int vx = (int)(vox % L.nvox[0]);
       const int vy = (int)((vox / L.nvox[0]) % L.nvox[1]);
       const int vz = (int)(vox / ((long long)L.nvox[0] * L.nvox[1]));
@@ -396,10 +408,22 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
   {
     StageTimer timer(ctx, 6);
     int blocks_e = (int)std::min<long long>((Le.nvoxels * 16 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
-    voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, index_of(E), Le, cnt_e, mom_e, occ);
+    const int pb_e = (int)std::min<long long>((E.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+    const int pb_g = (int)std::min<long long>((G.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+    if (Le.sparse) {
+      ME_CUDA(ctx, cudaMemsetAsync(cnt_e, 0, (size_t)Le.nvoxels * sizeof(int32_t), ctx->stream));
+      voxel_precount_kernel<<<pb_e, kThreads, 0, ctx->stream>>>(E.d_sorted, E.d_rel, E.n, index_of(E), Le, cnt_e);
+      ME_LAUNCH_CHECK(ctx);
+    }
+    if (Lg.sparse) {
+      ME_CUDA(ctx, cudaMemsetAsync(cnt_g, 0, (size_t)Lg.nvoxels * sizeof(int32_t), ctx->stream));
+      voxel_precount_kernel<<<pb_g, kThreads, 0, ctx->stream>>>(G.d_sorted, G.d_rel, G.n, index_of(G), Lg, cnt_g);
+      ME_LAUNCH_CHECK(ctx);
+    }
+    voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, index_of(E), Le, Le.sparse, cnt_e, mom_e, occ);
     ME_LAUNCH_CHECK(ctx);
     int blocks_g = (int)std::min<long long>((Lg.nvoxels * 16 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
-    voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, index_of(G), Lg, cnt_g, mom_g, occ + 1);
+    voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, index_of(G), Lg, Lg.sparse, cnt_g, mom_g, occ + 1);
     ME_LAUNCH_CHECK(ctx);
   }
   {

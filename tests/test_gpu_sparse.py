@@ -120,7 +120,7 @@ def test_site_scale_terrain(api, O):
     omme, oent = O.eval_mme(est, cfg["nn_radius"], 10, want_entropies=True)
     assert mme.n_valid == omme.n_valid and mme.n_valid > 0.9 * len(est)
     np.testing.assert_allclose(mme.mme, omme.mme, rtol=1e-7)
-    np.testing.assert_allclose(ent, oent, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(ent, oent, rtol=1e-6, atol=1e-6)      # entropies cross zero on this scene (r = 2 m): absolute floor
     oawd = O.eval_awd(est, gt, cfg["vmd_voxel_size"], 100, 5)
     assert awd.n_pairs == oawd.n_pairs and awd.n_pairs > 100
     np.testing.assert_allclose([awd.awd, awd.scs], [oawd.awd, oawd.scs], rtol=1e-8)
