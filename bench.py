@@ -261,7 +261,11 @@ def main():
             g_gt = torch.empty((world * m_gt, 3), dtype=torch.float64, device=dev)
             s_est = torch.empty((m_est, 3), dtype=torch.float64, device=dev)      # this rank's slice on the device
             s_gt = torch.empty((m_gt, 3), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream for everything: the library's kernels, torch's copies and the NCCL collectives are
+    # ordered on it (the legacy default stream has handle 0, which the C-ABI reads as "create your own stream" — torch's
+    # copies / collectives and the library's kernels would then race)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx = api.MapEvalB200(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream,
                           vmd_voxel_size=cfg["vmd_voxel_size"] if cfg["awd"] else 0.0)
 
