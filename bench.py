@@ -329,6 +329,7 @@ def main():
             ms = float(t.item())
         return ms / steps, ctx.launch_count() - l0, t0, t1
 
+    torch.cuda.synchronize()      # the clouds were produced on the default stream
     for _ in range(args.warmup):
         one_pass("device")
     stage_ms = {}
