@@ -259,6 +259,8 @@ int me_set_shard(me_ctx *ctx, int32_t rank, int32_t world) {
   ME_ENTER(ctx);
   if (world < 1 || rank < 0 || rank >= world) return fail(ctx, ME_ERR_INVALID, "bad rank/world");
   ctx->rank = rank; ctx->world = world;
+  ctx->slab_planned = false; ctx->slab_on = false;
+  ctx->cloud[0].grid_valid = ctx->cloud[1].grid_valid = false;      // slab lattices belong to one (rank, world)
   ctx->cloud[0].nn_valid = ctx->cloud[1].nn_valid = false;
   ctx->cloud[0].entropy_valid = ctx->cloud[1].entropy_valid = false;
   ctx->cloud[0].entropy_caller_valid = ctx->cloud[1].entropy_caller_valid = false;
@@ -284,6 +286,7 @@ int me_set_cloud(me_ctx *ctx, int which, const double *xyz_host, int64_t n) {
   c.owned = true;
   c.n = n;
   invalidate(c);
+  if (which == ME_CLOUD_EST) { ctx->slab_planned = false; ctx->slab_on = false; }
   if (n > 0) {
     // the copy runs on its own stream: it may overlap kernels that work on the other cloud, but must not overtake
     // kernels already queued that still read this buffer
@@ -318,6 +321,7 @@ int me_set_cloud_device(me_ctx *ctx, int which, const double *xyz_device, int64_
   c.upload_pending = false;
   c.n = n;
   invalidate(c);
+  if (which == ME_CLOUD_EST) { ctx->slab_planned = false; ctx->slab_on = false; }
   return ME_OK;
 }
 

@@ -58,6 +58,9 @@ struct CellIndex {
 
 struct Cloud {
   long long n = 0;
+  long long ns = 0;             // points in the sorted arrays: n, or the points of this rank's slab (+ halo) in slab mode
+  bool slab = false;            // the lattice holds only lattice planes [zc_lo, zc_hi); this rank owns the queries of [zo_lo, zo_hi)
+  int zo_lo = 0, zo_hi = 0, zc_lo = 0, zc_hi = 0;
   double *d_xyz = nullptr;      // caller order, fp64 AoS
   bool owned = false;
   long long cap_xyz = 0;
@@ -123,6 +126,11 @@ struct me_ctx {
   double nn_cell_size = 0.0;
   long long max_grid_cells = 0;     // budget of the dense cell table; 0 = automatic (grid_budget)
   double voxel_hint = 0.0;          // lattice alignment requested by the voxel stage
+  // slab mode (world > 1, dense lattices): every rank lays out only the voxel layers it owns (+ a halo of slab_halo cells) of
+  // both clouds instead of the whole clouds; planned from the estimated cloud's z histogram at its first build of a pass
+  bool slab_planned = false, slab_on = false;
+  long long slab_k0 = 0, slab_k1 = 0;      // owned world voxel layers [k0, k1) along z (LLONG_MIN / LLONG_MAX at the ends)
+  int slab_halo = 4;
   // lattice spec shared by both clouds, so that their cells coincide (same v, m; integer index offsets)
   double spec_v = 0.0;
   int spec_m = 0;

@@ -662,7 +662,7 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   if (c.grid_solo) {      // the solo lattice (and with it the sorted order of d_entropy) does not survive the next build
     ME_TRY(ensure(ctx, (void **)&c.d_entropy_caller, &c.cap_entropy_caller, c.n, sizeof(double)));
     const int blocks = (int)std::min<long long>((c.n + 255) / 256, (long long)ctx->sm_count * 16);
-    unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.n, c.d_entropy, c.d_entropy_caller);
+    unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.ns, c.d_entropy, c.d_entropy_caller);
     ME_LAUNCH_CHECK(ctx);
     c.entropy_caller_valid = true;
   }
@@ -680,7 +680,8 @@ int unsort_entropy(me_ctx *ctx, int which, double *h_entropy) {
   ME_TRY(ensure_work(ctx, (size_t)c.n * sizeof(double)));
   double *dst = (double *)ctx->d_work;
   int blocks = (int)std::min<long long>((c.n + 255) / 256, (long long)ctx->sm_count * 16);
-  unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.n, c.d_entropy, dst);
+  ME_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)c.n * sizeof(double), ctx->stream));      // slab mode: only this rank's points are written
+  unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.ns, c.d_entropy, dst);
   ME_LAUNCH_CHECK(ctx);
   ME_CUDA(ctx, cudaMemcpyAsync(h_entropy, dst, (size_t)c.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
