@@ -36,8 +36,18 @@ struct NNConst {
   int want_full_cd;
   double max_d2;        // nothing beyond this squared distance matters (inf when full CD is wanted)
   double ref_maxabs;    // max |coordinate| of the reference cloud (slack of the face test)
-  int cov_lo, cov_hi;   // lattice planes of the reference cloud laid out on this rank: [0, dimz) unless in slab mode
+  // slab layout: only the planes [cov_lo, cov_hi) of the reference lattice along axis cov_axis (1: y, 2: z; 0: everything)
+  // are laid out on this rank
+  int cov_axis, cov_lo, cov_hi, cov_dim;
 };
+
+// distance (in cells) from lattice coordinate (uy, uz) to the nearest plane of the reference lattice that is NOT laid out on
+// this rank: beyond it the cloud is unknown, not empty
+__device__ __forceinline__ double cover_dist_cells(const NNConst &C, double uy, double uz) {
+  if (C.cov_axis == 0) return INFINITY;
+  const double ua = C.cov_axis == 1 ? uy : uz;
+  return fmin(C.cov_lo > 0 ? ua - (double)C.cov_lo : INFINITY, C.cov_hi < C.cov_dim ? (double)C.cov_hi - ua : INFINITY);
+}
 
 // device accumulator block: 8 x int64 then 13 x fp64 (see me_nn_accum)
 struct AccBlock {
@@ -169,8 +179,7 @@ __device__ __forceinline__ void finish_query(const P4 &q, uint32_t i, long long 
                                              double *__restrict__ nn_sq, uint32_t *__restrict__ far_list,
                                              unsigned int *__restrict__ far_count, double ux, double uy, double uz,
                                              double slack_h) {
-  // beyond the planes laid out on this rank (slab mode) the cloud is unknown, not empty
-  const double gcov = fmin(C.cov_lo > 0 ? uz - (double)C.cov_lo : INFINITY, C.cov_hi < L.dims[2] ? (double)C.cov_hi - uz : INFINITY);
+  const double gcov = cover_dist_cells(C, uy, uz);
   const double g = fmin(fmin(fmin(face_dist_cells(ux, ix, 1, L.dims[0]), face_dist_cells(uy, iy, 1, L.dims[1])),
                              face_dist_cells(uz, iz, 1, L.dims[2])), gcov) * L.h;
   const double slack = slack_h * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
@@ -390,6 +399,7 @@ nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lat
 // ---------------------------------------------------------------------------------------------------------------
 struct FlatGeom {
   int qdimx, qdimy;            // query lattice (to decode the query's cell)
+  Owned own;                   // slab layout: the planes of the query lattice whose points this rank evaluates
   int q_sparse;                // the query cloud's tag holds the row id (sparse table) instead of the cell id
   int rdimx, rdimy, rdimz;     // reference lattice
   long long shx, shy, shz;     // reference cell = query cell + shift (the lattices share v and m)
@@ -415,6 +425,7 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
     const P4 q = load_p4(Q + i);      // needed after the walk only; issued here so its latency hides behind the walk
     const uint32_t cq = cell_of(q.idx);
     const uint32_t cyz = G.q_sparse ? cq : cq / (uint32_t)G.qdimx;      // row id z * dimy + y of the query's own lattice
+    if (!owns(G.own, (int)(cyz % (uint32_t)G.qdimy), (int)(cyz / (uint32_t)G.qdimy))) continue;      // a halo point
     // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
     const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
                     cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
@@ -510,11 +521,11 @@ nn_rows_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
   const long long stride = (long long)gridDim.x * kFlatThreads;
   for (long long base = q_begin + blockIdx.x * (long long)kFlatThreads; base < q_end; base += stride) {
     const long long i = base + threadIdx.x;
-    const bool live = i < q_end;
-    const long long il = live ? i : q_end - 1;
+    const long long il = i < q_end ? i : q_end - 1;
     const float4 qr = __ldg(qrel + il);
     const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + il) + 3)));
     const uint32_t cyz = G.q_sparse ? cq : cq / (uint32_t)G.qdimx;
+    const bool live = i < q_end && owns(G.own, (int)(cyz % (uint32_t)G.qdimy), (int)(cyz / (uint32_t)G.qdimy));
     // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
     const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
                     cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
@@ -626,8 +637,7 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, L
     double best = nn_d2[i];
     int bidx = nn_idx[i] >= 0 ? nn_idx[i] : 0x7fffffff;
     bool beyond = false, done = false, unresolved = false;
-    // slab mode: distance (in cells) to the nearest lattice plane that is NOT laid out on this rank
-    const double gcov = fmin(C.cov_lo > 0 ? uz - (double)C.cov_lo : INFINITY, C.cov_hi < L.dims[2] ? (double)C.cov_hi - uz : INFINITY);
+    const double gcov = cover_dist_cells(C, uy, uz);
     auto warp_argmin = [&]() {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -885,8 +895,9 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   C.accumulate = as_written ? 0 : 1;
   C.want_full_cd = p->want_full_cd ? 1 : 0;
   C.max_d2 = p->want_full_cd ? INFINITY : C.cutoff;
-  C.cov_lo = Rc.slab ? Rc.zc_lo : 0;
-  C.cov_hi = Rc.slab ? Rc.zc_hi : Rc.lat.dims[2];
+  C.cov_axis = Rc.slab ? Rc.sl_axis : 0;
+  C.cov_lo = Rc.sc_lo; C.cov_hi = Rc.sc_hi;
+  C.cov_dim = Rc.slab ? Rc.lat.dims[Rc.sl_axis] : 0;
   C.ref_maxabs = 0;
   for (int a = 0; a < 3; ++a) C.ref_maxabs = std::max(C.ref_maxabs, std::max(std::fabs(Rc.bbox_min[a]), std::fabs(Rc.bbox_max[a])));
 
@@ -896,6 +907,8 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
                                         3 * Rc.max_cell_count >= (1 << 24));
   if (any_sparse && 3 * Rc.max_cell_count >= (1 << 24))
     return fail(ctx, ME_ERR_RANGE, "more than 2^24 / 3 points in one lattice cell of a sparse lattice");
+  if (use_tile && (Qc.slab || Rc.slab))
+    return fail(ctx, ME_ERR_RANGE, "the tile sweep cannot run on a slab layout (use ME_LAYOUT_REPLICATED for this data)");
   long long qb, qe, tb = 0, te = 0;
   ME_TRY(query_shard(ctx, qwhich, &qb, &qe));  // flat sweep: contiguous, cell-aligned range of the cell-sorted query order
   if (use_tile) {                              // (before the work buffer is carved up: the tile build scans in it)
@@ -936,6 +949,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       FlatGeom G;
       G.qdimx = Qc.lat.dims[0]; G.qdimy = Qc.lat.dims[1];
       G.q_sparse = Qc.lat.sparse;
+      G.own = owned_of(Qc);
       G.rdimx = Rc.lat.dims[0]; G.rdimy = Rc.lat.dims[1]; G.rdimz = Rc.lat.dims[2];
       G.shx = (long long)(Qc.lat.k_lo[0] - Rc.lat.k_lo[0]) * Qc.lat.m;
       G.shy = (long long)(Qc.lat.k_lo[1] - Rc.lat.k_lo[1]) * Qc.lat.m;
@@ -994,7 +1008,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     ME_LAUNCH_CHECK(ctx);
   }
   if (to_block) {      // the accumulators stay on the device (all-reduced there, fetched once per pass)
-    pack_nn_kernel<<<1, 32, 0, ctx->stream>>>(acc, (sharded && use_tile) ? n_eval : nullptr, sharded ? qe - qb : Qc.n,
+    pack_nn_kernel<<<1, 32, 0, ctx->stream>>>(acc, (sharded && use_tile) ? n_eval : nullptr, Qc.slab ? Qc.n_owned : (sharded ? qe - qb : Qc.n),
                                               ctx->d_block + (qwhich == ME_CLOUD_EST ? 0 : kBlkNN));
     ME_LAUNCH_CHECK(ctx);
     Qc.nn_valid = true;
@@ -1006,7 +1020,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   if (sharded && use_tile) ME_CUDA(ctx, cudaMemcpyAsync(h_eval, n_eval, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::memset(out, 0, sizeof(*out));
-  out->n_query = !sharded ? Qc.n : (use_tile ? (int64_t)*h_eval : qe - qb);
+  out->n_query = !sharded ? Qc.n : (use_tile ? (int64_t)*h_eval : (Qc.slab ? Qc.n_owned : qe - qb));
   out->n_corr = (int64_t)h->n_corr;
   for (int k = 0; k < 5; ++k) { out->n_inlier[k] = (int64_t)h->n_inl[k]; out->sum_d[k] = h->sum_d[k]; out->sum_d2[k] = h->sum_d2[k]; }
   out->n_ub = (int64_t)h->n_ub;
