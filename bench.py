@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; not a bench line)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="slab", choices=["slab", "replicated"],
+                    help="N > 1: slab = every rank lays out only the voxel layers it owns (default); replicated = whole clouds on every rank")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arms (large configs on small hosts)")
     ap.add_argument("--gen", default="auto", choices=["auto", "numpy", "device"],
                     help="where the synthetic clouds are generated (auto: on the device above 20 M points)")
@@ -268,6 +270,10 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = api.MapEvalB200(device=local_rank, rank=rank, world=world, stream=stream.cuda_stream,
                           vmd_voxel_size=cfg["vmd_voxel_size"] if cfg["awd"] else 0.0)
+    # N > 1: slab layout — every rank lays out (and evaluates) only the voxel layers it owns of both clouds; the library
+    # keeps the replicated layout where the scene cannot be cut (ctx.layout_active() tells which one ran)
+    if world > 1 and args.layout == "slab":
+        ctx.set_layout(A.ME_LAYOUT_SLAB)
 
     results = {}
 
@@ -295,10 +301,22 @@ def main():
             if cfg["gt_mme"]:
                 ctx.eval_mme_accum_device(A.ME_CLOUD_GT, cfg["nn_radius"], 5)
         ctx.eval_nn_accum_device(p)
-        awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5) if cfg["awd"] else None
+        awd = None
+        slab = world > 1 and ctx.layout_active()["layout"] == A.ME_LAYOUT_SLAB
+        if cfg["awd"] and slab:
+            # every rank computes the voxels of its layers; the W table is MAX-all-reduced for the SCS neighbourhoods and
+            # the stage's counters / sums ride in the accumulator block
+            ctx.voxel_begin(cfg["vmd_voxel_size"], 100)
+            mdist.allreduce_voxel_w(ctx, dev)
+            ctx.voxel_finish_accum_device(5)
+        elif cfg["awd"]:
+            awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 100, 5)
         if world > 1:
             mdist.allreduce_block(ctx, dev)
         nn_e, nn_g, mmes = ctx.accum_fetch(want_mme=(bool(cfg["mme"]), bool(cfg["mme"] and cfg["gt_mme"])))
+        if cfg["awd"] and slab:
+            awd = ctx.accum_fetch_awd()
+        results["layout"] = ctx.layout_active()
         results["nn"] = ctx.nn_finalize(p, nn_e, nn_g)
         results["mme"] = [ctx.mme_finalize(m, w) for m, w in zip(mmes, (A.ME_CLOUD_EST, A.ME_CLOUD_GT))]
         results["awd"] = awd
@@ -352,7 +370,9 @@ def main():
         # dominant kernel: the MME radius sweep of the estimated map (stage "mme_est" = the sweep kernel + a 1-thread init).
         # algorithmic bytes per launch: 12 B query + 12 B reference + 8 B entropy out per point of this
         # rank's query range
-        nq = n_est * (rank + 1) // world - n_est * rank // world
+        lay = results.get("layout") or {}
+        slab = lay.get("layout") == A.ME_LAYOUT_SLAB
+        nq = lay["n_owned"][0] if slab else n_est * (rank + 1) // world - n_est * rank // world
         dom = "mme_est" if cfg["mme"] else "nn_est_to_gt"
         alg_bytes = (32.0 * nq) if cfg["mme"] else (12.0 * (nq + n_gt))
         dom_ms = stage_ms.get(dom, 0.0)
@@ -406,7 +426,10 @@ def main():
                        "n_gt": n_gt, "tau": cfg["tau"], "icp_max_distance": 1.0, "nn_radius": cfg["nn_radius"],
                        "vmd_voxel_size": cfg["vmd_voxel_size"], "mme_gt": bool(cfg["gt_mme"]),
                        "generated": gen,
-                       "parallelism": f"query-range shard x{world}, lattices replicated",
+                       "parallelism": (f"slab layout x{world}: voxel layers along {'xyz'[lay.get('axis', 0)]} owned per rank, lattice builds, "
+                                       f"sweeps and voxel stage sharded; rank 0 lays out {lay['n_laid_out'][0]} + {lay['n_laid_out'][1]} "
+                                       f"points and evaluates {lay['n_owned'][0]} + {lay['n_owned'][1]}") if slab else
+                                      f"query-range shard x{world}, lattices replicated",
                        "l2": f"inputs per pass ({24 * (n_est + n_gt) / 1e6:.0f} MB of fp64 clouds, {48 * (n_est + n_gt) / 1e6:.0f} MB of "
                              "sorted records and fp32 screening copies) exceed the 126 MB L2 several times over; no flush needed"},
             "e2e": e2e,

@@ -20,6 +20,8 @@ ME_CUTOFF_DIST_LT_R = 1
 ME_PAIRING_AS_WRITTEN = 0
 ME_PAIRING_GEOMETRIC = 1
 
+ME_LAYOUT_REPLICATED = 0
+ME_LAYOUT_SLAB = 1
 ME_ICP_POINT_TO_POINT = 0
 ME_ICP_POINT_TO_PLANE = 1
 ME_ICP_GENERALIZED = 2

@@ -245,6 +245,36 @@ class MapEvalB200:
                                            C.byref(mm[1]) if mm[1] else None))
         return e, g, [m for m in mm if m is not None]
 
+    # -- layouts of a multi-GPU job; the voxel stage in two halves ------------------------------------------------
+    def set_layout(self, layout):
+        """A.ME_LAYOUT_REPLICATED (default) or A.ME_LAYOUT_SLAB: every rank lays out only the voxel layers it owns."""
+        self._check(self._L.me_set_layout(self._ctx, int(layout)))
+
+    def layout_active(self):
+        """{'layout', 'axis', 'n_laid_out': [est, gt], 'n_owned': [est, gt]} once the lattices are built"""
+        lay, ax = C.c_int32(0), C.c_int32(0)
+        nl, no = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+        self._check(self._L.me_layout_active(self._ctx, C.byref(lay), C.byref(ax), nl, no))
+        return {"layout": lay.value, "axis": ax.value, "n_laid_out": list(nl), "n_owned": list(no)}
+
+    def voxel_begin(self, voxel_size, min_points=100):
+        self._check(self._L.me_voxel_begin(self._ctx, float(voxel_size), int(min_points)))
+
+    def voxel_w_table(self):
+        """(device pointer, n) of the W table over the estimated cloud's voxels (-1 = no pair)"""
+        ptr = C.POINTER(C.c_double)()
+        n = C.c_int64(0)
+        self._check(self._L.me_voxel_w_table(self._ctx, C.byref(ptr), C.byref(n)))
+        return C.cast(ptr, C.c_void_p).value, n.value
+
+    def voxel_finish_accum_device(self, scs_radius=5):
+        self._check(self._L.me_voxel_finish_accum_device(self._ctx, int(scs_radius)))
+
+    def accum_fetch_awd(self):
+        out = A.me_awd_result()
+        self._check(self._L.me_accum_fetch_awd(self._ctx, C.byref(out)))
+        return out
+
     # -- introspection -----------------------------------------------------------------------------------------
     def stage_times_ms(self):
         ms = (C.c_double * A.ME_N_STAGE_TIMES)()

@@ -259,10 +259,39 @@ int me_set_shard(me_ctx *ctx, int32_t rank, int32_t world) {
   ME_ENTER(ctx);
   if (world < 1 || rank < 0 || rank >= world) return fail(ctx, ME_ERR_INVALID, "bad rank/world");
   ctx->rank = rank; ctx->world = world;
+  ctx->slab_planned = false; ctx->slab_on = false; ctx->vox_open = false;
+  ctx->cloud[0].grid_valid = ctx->cloud[1].grid_valid = false;      // slab lattices belong to one (rank, world)
   ctx->cloud[0].nn_valid = ctx->cloud[1].nn_valid = false;
   ctx->cloud[0].entropy_valid = ctx->cloud[1].entropy_valid = false;
   ctx->cloud[0].entropy_caller_valid = ctx->cloud[1].entropy_caller_valid = false;
   ctx->cloud[0].shard_valid = ctx->cloud[1].shard_valid = false;
+  return ME_OK;
+}
+
+int me_set_layout(me_ctx *ctx, int32_t layout) {
+  ME_ENTER(ctx);
+  if (layout != ME_LAYOUT_REPLICATED && layout != ME_LAYOUT_SLAB) return fail(ctx, ME_ERR_INVALID, "bad layout");
+  const bool want = layout == ME_LAYOUT_SLAB;
+  if (want == ctx->slab_request) return ME_OK;
+  ctx->slab_request = want;
+  ctx->slab_planned = false; ctx->slab_on = false; ctx->vox_open = false;
+  for (int w = 0; w < 2; ++w) {      // the lattices are laid out again under the new layout
+    ctx->cloud[w].grid_valid = false; ctx->cloud[w].nn_valid = false; ctx->cloud[w].entropy_valid = false;
+    ctx->cloud[w].shard_valid = false;
+  }
+  return ME_OK;
+}
+
+int me_layout_active(me_ctx *ctx, int32_t *layout, int32_t *axis, int64_t n_laid_out[2], int64_t n_owned[2]) {
+  ME_ENTER(ctx);
+  const bool slab = (ctx->cloud[0].grid_valid && ctx->cloud[0].slab) || (ctx->cloud[1].grid_valid && ctx->cloud[1].slab);
+  if (layout) *layout = slab ? ME_LAYOUT_SLAB : ME_LAYOUT_REPLICATED;
+  if (axis) *axis = slab ? ctx->slab_axis : 0;
+  for (int w = 0; w < 2; ++w) {
+    const Cloud &c = ctx->cloud[w];
+    if (n_laid_out) n_laid_out[w] = c.grid_valid ? c.ns : 0;
+    if (n_owned) n_owned[w] = c.grid_valid ? c.n_owned : 0;
+  }
   return ME_OK;
 }
 
@@ -442,6 +471,39 @@ int me_accum_block(me_ctx *ctx, double **device_block, int32_t *n_sum, int32_t *
   if (device_block) *device_block = ctx->d_block;
   if (n_sum) *n_sum = kBlkSumCount;
   if (n_max) *n_max = kBlkMaxCount;
+  return ME_OK;
+}
+
+int me_voxel_begin(me_ctx *ctx, double voxel_size, int32_t min_points) {
+  ME_ENTER(ctx);
+  return voxel_begin(ctx, voxel_size, min_points);
+}
+
+int me_voxel_w_table(me_ctx *ctx, double **device_w, int64_t *n) {
+  ME_ENTER(ctx);
+  if (!device_w || !n) return fail(ctx, ME_ERR_INVALID, "null argument");
+  return voxel_w_table(ctx, device_w, n);
+}
+
+int me_voxel_finish_accum_device(me_ctx *ctx, int32_t scs_radius) {
+  ME_ENTER(ctx);
+  return voxel_finish_block(ctx, scs_radius);
+}
+
+int me_accum_fetch_awd(me_ctx *ctx, me_awd_result *out) {
+  ME_ENTER(ctx);
+  if (!out) return fail(ctx, ME_ERR_INVALID, "null result");
+  double *h = (double *)((char *)ctx->h_pinned + 3072);
+  ME_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_block + kBlkAwd, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  auto i64 = [](double v) { return (int64_t)std::llround(v); };
+  std::memset(out, 0, sizeof(*out));
+  out->n_pairs = i64(h[0]); out->n_scs = i64(h[1]);
+  out->n_voxels_est = i64(h[2]); out->n_voxels_gt = i64(h[3]);
+  out->n_active = i64(h[4]); out->n_new = i64(h[5]);
+  out->n_old = out->n_voxels_gt - out->n_active;
+  out->awd = h[6] / (double)out->n_pairs;        // 0/0 -> NaN as map_eval.cpp:324
+  out->scs = h[7] / (double)out->n_scs;          // map_eval.cpp:387
   return ME_OK;
 }
 

@@ -58,6 +58,12 @@ struct CellIndex {
 
 struct Cloud {
   long long n = 0;
+  long long ns = 0;             // points in the sorted arrays: n, or the points of this rank's slab (+ halo) in slab mode
+  // slab layout: only the lattice planes [sc_lo, sc_hi) along lattice axis sl_axis (1: y, 2: z) are laid out here, and this
+  // rank owns the queries of the planes [so_lo, so_hi) — n_owned points; the sweeps skip the halo points
+  bool slab = false;
+  int sl_axis = 0, so_lo = 0, so_hi = 0, sc_lo = 0, sc_hi = 0;
+  long long n_owned = 0;
   double *d_xyz = nullptr;      // caller order, fp64 AoS
   bool owned = false;
   long long cap_xyz = 0;
@@ -123,6 +129,17 @@ struct me_ctx {
   double nn_cell_size = 0.0;
   long long max_grid_cells = 0;     // budget of the dense cell table; 0 = automatic (grid_budget)
   double voxel_hint = 0.0;          // lattice alignment requested by the voxel stage
+  // slab layout (me_set_layout, world > 1, dense lattices): every rank lays out only the voxel layers it owns (+ a halo of
+  // slab_halo cells) of both clouds instead of the whole clouds; planned from the layer histogram of the cloud that is laid
+  // out first after the lattice spec was (re)planned — identical on every rank, the clouds being replicated
+  bool slab_request = false, slab_planned = false, slab_on = false;
+  int slab_axis = 0;                       // 1: y, 2: z
+  long long slab_k0 = 0, slab_k1 = 0;      // owned world voxel layers [k0, k1) along slab_axis (LLONG_MIN/4, LLONG_MAX/4 at the ends)
+  int slab_halo = 4;                       // cells; covers the 3 rings of an MME sweep on the shared lattice
+  // voxel stage split in two (me_voxel_begin / me_voxel_finish_accum_device): state kept between the halves
+  bool vox_open = false;
+  long long vox_nvox = 0;
+  size_t vox_o_w = 0, vox_o_pairs = 0;
   // lattice spec shared by both clouds, so that their cells coincide (same v, m; integer index offsets)
   double spec_v = 0.0;
   int spec_m = 0;
@@ -189,6 +206,22 @@ struct StageTimer {
   ~StageTimer() { cudaEventRecord(ctx->ev[2 * stage + 1], ctx->stream); ctx->ev_used[stage] = true; }
 };
 
+// the queries a sweep evaluates: all of [q_begin, q_end), or in slab layout those whose cell lies in the owned planes
+struct Owned {
+  int axis;      // 0: everything, 1: y, 2: z
+  int lo, hi;
+};
+__host__ __device__ inline bool owns(const Owned &o, int iy, int iz) {
+  if (o.axis == 0) return true;
+  const int a = o.axis == 1 ? iy : iz;
+  return a >= o.lo && a < o.hi;
+}
+inline Owned owned_of(const Cloud &c) {
+  Owned o;
+  o.axis = c.slab ? c.sl_axis : 0; o.lo = c.so_lo; o.hi = c.so_hi;
+  return o;
+}
+
 // coarse occupancy grid of a lattice (grid.cu build_coarse): cnt[(cz * cd[1] + cy) * cd[0] + cx] points in the block of f^3 cells
 struct CoarseGrid {
   const uint32_t *cnt;      // nullptr: none
@@ -231,13 +264,17 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
 // below 2^53, so their sums are exact and order-independent).
 static constexpr int kBlkNN = 22;                    // per direction: n_query n_corr n_inlier[5] n_ub n_far | sum_d[5] sum_d2[5] sum_d_all sum_d2_all sum_nn
 static constexpr int kBlkMmeSum = 2 * kBlkNN;        // per cloud: n_query n_valid sum_entropy
-static constexpr int kBlkSumCount = kBlkMmeSum + 6;  // = 50 SUM values
+static constexpr int kBlkAwd = kBlkMmeSum + 6;       // voxel stage: n_pairs n_scs n_voxels_est n_voxels_gt n_active n_new sum_w sum_scs
+static constexpr int kBlkSumCount = kBlkAwd + 8;     // = 58 SUM values
 static constexpr int kBlkMax = kBlkSumCount;         // per cloud: max_entropy, -min_entropy
 static constexpr int kBlkMaxCount = 4;
 static constexpr int kBlkTotal = kBlkSumCount + kBlkMaxCount;
 int unsort_entropy(me_ctx *ctx, int which, double *h_entropy);
 int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
             double **rows27);
+int voxel_begin(me_ctx *ctx, double voxel_size, int min_points);
+int voxel_w_table(me_ctx *ctx, double **d_w, int64_t *n);
+int voxel_finish_block(me_ctx *ctx, int scs_radius);
 int transform_cloud(me_ctx *ctx, int which, const double T[16]);
 int run_icp(me_ctx *ctx, int method, double max_dist, int max_iter, double rel_fitness, double rel_rmse, const double T_init[16],
             me_icp_result *out);

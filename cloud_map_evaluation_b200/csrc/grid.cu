@@ -8,6 +8,7 @@
 // grids sized in multiples of the SM count, no tensor cores.
 #include "common.cuh"
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -231,9 +232,14 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(uint32_t *__restri
 __global__ void __launch_bounds__(kThreads) scatter_kernel(const double *__restrict__ xyz, long long n,
                                                            const uint32_t *__restrict__ cell_id,
                                                            uint32_t *__restrict__ cell_cursor,
-                                                           P4 *__restrict__ sorted) {
+                                                           P4 *__restrict__ sorted, int axis, int dimx, int dimy, int c_lo, int c_hi) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     uint32_t c = __ldg(cell_id + i);
+    if (axis) {      // slab layout: points outside this rank's planes are not laid out
+      const uint32_t row = c / (uint32_t)dimx;
+      const int a = axis == 2 ? (int)(row / (uint32_t)dimy) : (int)(row % (uint32_t)dimy);
+      if (a < c_lo || a >= c_hi) continue;
+    }
     uint32_t slot = atomicAdd(cell_cursor + c, 1u);
     double x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
     double2 *o = reinterpret_cast<double2 *>(sorted + slot);
@@ -339,6 +345,7 @@ __global__ void shard_bounds_kernel(const P4 *__restrict__ sorted, const float4 
 int query_shard(me_ctx *ctx, int which, long long *b, long long *e) {
   Cloud &c = ctx->cloud[which];
   if (ctx->world == 1) { *b = 0; *e = c.n; return ME_OK; }
+  if (c.slab) { *b = 0; *e = c.ns; return ME_OK; }      // slab layout: the sweeps walk what is laid out here and skip the halo (Owned)
   if (!(c.shard_valid && c.shard_rank == ctx->rank && c.shard_world == ctx->world)) {
     unsigned long long *d = (unsigned long long *)ctx->d_scratch + 12, *h = (unsigned long long *)ctx->h_pinned + 12;
     shard_bounds_kernel<<<1, 32, 0, ctx->stream>>>(c.d_sorted, c.d_rel, index_of(c), c.n, ctx->rank, ctx->world, d);
@@ -644,12 +651,137 @@ static int build_coarse(me_ctx *ctx, Cloud &c) {
   for (int a = 0; a < 3; ++a) { c.coarse_dims[a] = (L.dims[a] + f - 1) >> shift; ncoarse *= c.coarse_dims[a]; }
   ME_TRY(ensure(ctx, (void **)&c.d_coarse, &c.cap_coarse, ncoarse, sizeof(uint32_t)));
   ME_CUDA(ctx, cudaMemsetAsync(c.d_coarse, 0, (size_t)ncoarse * sizeof(uint32_t), ctx->stream));
-  const int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-  coarse_count_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.d_rel, c.n, index_of(c), shift, c.coarse_dims[0],
+  const int blocks = (int)std::min<long long>((c.ns + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+  coarse_count_kernel<<<std::max(1, blocks), kThreads, 0, ctx->stream>>>(c.d_sorted, c.d_rel, c.ns, index_of(c), shift, c.coarse_dims[0],
                                                           c.coarse_dims[1], c.d_coarse);
   ME_LAUNCH_CHECK(ctx);
   c.coarse_f = f;
   return ME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// slab layout (me_set_layout, world > 1, dense lattices).  The query ranges of the sweeps are sharded anyway; laying out BOTH
+// WHOLE clouds on every rank is what bounds strong scaling (1.45 ms of a 3.9 ms pass on 8 GPUs).  In slab layout
+// a rank lays out only the lattice planes of the voxel layers it owns along one lattice axis (y or z, whichever balances —
+// terrestrial scans are flat in z), plus slab_halo cells on either side, of both clouds: the histogram still covers the whole
+// cloud (a streaming pass), the counts outside the slab are cleared, and the expensive random-write scatter touches about
+// 1/W of the points.  The layers are balanced on the layer histogram of the cloud laid out first and are expressed in WORLD
+// voxel indices, so the slabs of the two clouds coincide and every voxel has one owner.  The sweeps walk the laid-out points
+// and skip the halo ones (Owned); searches that would leave the halo are finished by brute force over the caller-order
+// cloud (nn.cu).
+// ---------------------------------------------------------------------------------------------------------------
+// out[p] = points in lattice plane p along `axis` (1: y, 2: z)
+__global__ void __launch_bounds__(kThreads) plane_count_kernel(const uint32_t *__restrict__ count, int dimx, int dimy, int dimz,
+                                                               int axis, unsigned long long *__restrict__ out) {
+  __shared__ unsigned long long ws[kThreads / 32];
+  const int np = axis == 2 ? dimz : dimy;
+  for (int p = blockIdx.x; p < np; p += gridDim.x) {
+    unsigned long long s = 0;
+    if (axis == 2) {
+      const long long pl = (long long)dimx * dimy;
+      const uint32_t *q = count + (long long)p * pl;
+      for (long long i = threadIdx.x; i < pl; i += kThreads) s += __ldg(q + i);
+    } else {
+      for (int z = 0; z < dimz; ++z) {
+        const uint32_t *q = count + ((long long)z * dimy + p) * dimx;
+        for (int i = threadIdx.x; i < dimx; i += kThreads) s += __ldg(q + i);
+      }
+    }
+    s = (unsigned long long)warp_sum_ll((long long)s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < kThreads / 32; ++w) t += ws[w]; out[p] = t; }
+    __syncthreads();
+  }
+}
+
+// clear the counts of the cells outside the covered planes; out[0] += points in the owned planes
+__global__ void __launch_bounds__(kThreads) slab_mask_kernel(uint32_t *__restrict__ count, long long ncells, int dimx, int dimy,
+                                                             int axis, int c_lo, int c_hi, int o_lo, int o_hi,
+                                                             unsigned long long *__restrict__ out) {
+  unsigned long long own = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncells; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / dimx;
+    const int a = axis == 2 ? (int)(row / dimy) : (int)(row % dimy);
+    if (a < c_lo || a >= c_hi) count[i] = 0u;
+    else if (a >= o_lo && a < o_hi) own += __ldg(count + i);
+  }
+  own = (unsigned long long)warp_sum_ll((long long)own);
+  if ((threadIdx.x & 31) == 0 && own) atomicAdd(out, own);
+}
+
+static bool slab_wanted(const me_ctx *ctx) { return ctx->slab_request && ctx->world > 1 && getenv("ME_NO_SLAB") == nullptr; }
+
+// plan the owned voxel layers of every rank from the layer histograms of cloud c (histogram in c.d_cell_off + 1); the same
+// arithmetic on the same (replicated) cloud on every rank gives the same plan
+static int plan_slabs(me_ctx *ctx, Cloud &c, const Lattice &L) {
+  ctx->slab_planned = true;
+  ctx->slab_on = false;
+  const int W = ctx->world, H = ctx->slab_halo;
+  const int np = L.dims[1] + L.dims[2];
+  ME_TRY(ensure_work(ctx, (size_t)np * sizeof(unsigned long long)));
+  unsigned long long *d_pl = (unsigned long long *)ctx->d_work;
+  plane_count_kernel<<<std::min(L.dims[1], ctx->sm_count * 8), kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.dims[0], L.dims[1], L.dims[2], 1, d_pl);
+  ME_LAUNCH_CHECK(ctx);
+  plane_count_kernel<<<std::min(L.dims[2], ctx->sm_count * 8), kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.dims[0], L.dims[1], L.dims[2], 2, d_pl + L.dims[1]);
+  ME_LAUNCH_CHECK(ctx);
+  std::vector<unsigned long long> h((size_t)np);
+  ME_CUDA(ctx, cudaMemcpyAsync(h.data(), d_pl, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double best_share = 2.0;
+  std::vector<int> best_b;
+  int best_axis = 0;
+  for (int axis = 1; axis <= 2; ++axis) {
+    const int nl = L.nvox[axis];
+    if (nl < 2 * W) continue;                            // too few voxel layers to cut
+    const unsigned long long *hp = h.data() + (axis == 2 ? L.dims[1] : 0);
+    std::vector<unsigned long long> cum((size_t)nl * L.m + 1, 0);      // per plane
+    for (int p = 0; p < nl * L.m; ++p) cum[p + 1] = cum[p] + hp[p];
+    const unsigned long long total = cum[(size_t)nl * L.m];
+    if (total == 0) continue;
+    std::vector<int> b((size_t)W + 1, 0);
+    b[W] = nl;
+    for (int r = 1; r < W; ++r) {
+      const unsigned long long want = total / (unsigned long long)W * (unsigned long long)r;
+      int lo = b[r - 1] + 1, hi = nl - (W - r);
+      int l = lo;
+      while (l < hi && cum[(size_t)l * L.m] < want) ++l;      // first layer boundary at or past the target
+      if (l > lo && want - cum[(size_t)(l - 1) * L.m] < cum[(size_t)l * L.m] - want) --l;
+      b[r] = l;
+    }
+    // the share of the cloud the busiest rank lays out (owned layers + halo)
+    unsigned long long worst = 0;
+    for (int r = 0; r < W; ++r) {
+      const int p0 = std::max(0, b[r] * L.m - H), p1 = std::min(nl * L.m, b[r + 1] * L.m + H);
+      worst = std::max(worst, cum[p1] - cum[p0]);
+    }
+    const double share = (double)worst / (double)total;
+    if (share < best_share) { best_share = share; best_b = b; best_axis = axis; }
+  }
+  // worth it only if the busiest rank lays out clearly less than the whole cloud
+  if (best_axis == 0 || best_share > 0.75) return ME_OK;
+  const int r = ctx->rank;
+  ctx->slab_axis = best_axis;
+  ctx->slab_k0 = r == 0 ? LLONG_MIN / 4 : (long long)L.k_lo[best_axis] + best_b[r];
+  ctx->slab_k1 = r == W - 1 ? LLONG_MAX / 4 : (long long)L.k_lo[best_axis] + best_b[r + 1];
+  ctx->slab_on = true;
+  return ME_OK;
+}
+
+// owned / covered lattice planes of cloud c on lattice L for the planned layers
+static void slab_planes(const me_ctx *ctx, const Lattice &L, Cloud &c) {
+  const int ax = ctx->slab_axis, dim = L.dims[ax];
+  auto plane = [&](long long k) -> int {
+    if (k <= LLONG_MIN / 8) return 0;
+    if (k >= LLONG_MAX / 8) return dim;
+    const long long z = (k - (long long)L.k_lo[ax]) * L.m;
+    return (int)std::min<long long>(std::max<long long>(z, 0), dim);
+  };
+  c.sl_axis = ax;
+  c.so_lo = plane(ctx->slab_k0); c.so_hi = plane(ctx->slab_k1);
+  if (c.so_lo >= c.so_hi) { c.sc_lo = c.sc_hi = c.so_hi = c.so_lo; return; }      // nothing of this cloud here
+  c.sc_lo = std::max(0, c.so_lo - ctx->slab_halo);
+  c.sc_hi = std::min(dim, c.so_hi + ctx->slab_halo);
 }
 
 // solo_h > 0: lay the cloud out on a lattice of its own with cells of (about) that edge — used by the MME sweep when the
@@ -690,6 +822,7 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     if (o.grid_valid && !o.grid_solo) {   // the other grid's spec cannot host this cloud: both are laid out again
       o.grid_valid = false; o.nn_valid = false; o.entropy_valid = false;
     }
+    ctx->slab_planned = false;              // the slabs are planned again with the spec
     const Cloud *other = (o.n > 0 && o.bbox_valid) ? &o : nullptr;
     double h_target = ctx->nn_cell_size > 0 ? ctx->nn_cell_size : density_edge(c);
     bool have = false;
@@ -726,6 +859,29 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
   c.solo_h = solo ? solo_h : 0.0;
   c.lat = L;
 
+  c.slab = false;
+  c.ns = c.n;
+  c.n_owned = c.n;
+  if (!built && !solo && slab_wanted(ctx)) {
+    if (!ctx->slab_planned) ME_TRY(plan_slabs(ctx, c, L));
+    if (ctx->slab_on) {
+      slab_planes(ctx, L, c);
+      unsigned long long *d_own = (unsigned long long *)ctx->d_scratch + 11;
+      ME_CUDA(ctx, cudaMemsetAsync(d_own, 0, sizeof(unsigned long long), ctx->stream));
+      const int mb = (int)std::min<long long>((L.ncells + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+      slab_mask_kernel<<<mb, kThreads, 0, ctx->stream>>>(c.d_cell_off + 1, L.ncells, L.dims[0], L.dims[1], c.sl_axis, c.sc_lo, c.sc_hi,
+                                                        c.so_lo, c.so_hi, d_own);
+      ME_LAUNCH_CHECK(ctx);
+      c.slab = true;
+    }
+  } else if (built && !solo && slab_wanted(ctx)) {
+    // a sparse lattice is laid out whole: the pass falls back to replicated lattices (the other cloud is laid out again)
+    ctx->slab_planned = true;
+    if (ctx->slab_on) {
+      ctx->slab_on = false;
+      if (o.slab && o.grid_valid) { o.grid_valid = false; o.nn_valid = false; o.entropy_valid = false; }
+    }
+  }
   if (!built) {
     // scratch slots: [9] occupied cells, [10] largest cell (bounds the run lengths of the sweeps)
     unsigned long long *d_nt = (unsigned long long *)ctx->d_scratch + 8;
@@ -744,10 +900,24 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     ME_TRY(ensure(ctx, (void **)&c.d_sorted, &c.cap_sorted, c.n, sizeof(P4)));
     ME_TRY(ensure(ctx, (void **)&c.d_rel, &c.cap_rel, c.n, sizeof(float4)));
     int blocks = (int)std::min<long long>((c.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
-    scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted);
+    scatter_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_xyz, c.n, c.d_cell_id, c.d_cell_off + 1, c.d_sorted, c.slab ? c.sl_axis : 0,
+                                                        L.dims[0], L.dims[1], c.sc_lo, c.sc_hi);
     ME_LAUNCH_CHECK(ctx);
-    rel_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, c.n, L, c.d_rel);
-    ME_LAUNCH_CHECK(ctx);
+    if (c.slab) {
+      // the scatter leaves off[] a CSR array: its last entry = the points laid out here
+      uint32_t *h_sl = (uint32_t *)((unsigned long long *)ctx->h_pinned + 16);
+      unsigned long long *h_own = (unsigned long long *)ctx->h_pinned + 11;
+      ME_CUDA(ctx, cudaMemcpyAsync(h_sl, c.d_cell_off + L.ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      ME_CUDA(ctx, cudaMemcpyAsync(h_own, (unsigned long long *)ctx->d_scratch + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      c.ns = (long long)h_sl[0];
+      c.n_owned = (long long)*h_own;
+    }
+    {
+      const int rb = (int)std::min<long long>((c.ns + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
+      rel_kernel<<<std::max(1, rb), kThreads, 0, ctx->stream>>>(c.d_sorted, c.ns, L, c.d_rel);
+      ME_LAUNCH_CHECK(ctx);
+    }
     ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     c.max_cell_count = (long long)h_nt[2];
   }

@@ -395,6 +395,7 @@ int estimate_normals(me_ctx *ctx, int which, int knn, int gicp) {
   if (c.n <= 0) return fail(ctx, ME_ERR_EMPTY, "cloud is empty");
   if (knn < 1 || knn > 64) return fail(ctx, ME_ERR_INVALID, "knn must be in 1..64");
   ME_TRY(build_grid(ctx, which, c.grid_valid && c.grid_solo ? c.solo_h : 0.0));
+  if (c.slab) return fail(ctx, ME_ERR_INVALID, "me_estimate_normals needs the replicated layout (ME_LAYOUT_REPLICATED)");
   ME_TRY(ensure(ctx, (void **)&c.d_normal, &c.cap_normal, 3 * c.n, sizeof(double)));
   const int k = (int)std::min<long long>(knn, c.n);
   const size_t smem = (size_t)k * kKnnThreads * (sizeof(double) + sizeof(uint32_t));

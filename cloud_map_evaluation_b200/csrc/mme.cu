@@ -146,13 +146,18 @@ __device__ __forceinline__ void walk_global(const P4 &q, const P4 *__restrict__ 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 mme_kernel(const P4 *__restrict__ S, long long q_begin, long long q_end, CellIndex I,
-           Lattice L, double r2, float rc2, int rings, int min_neighbors, double *__restrict__ entropy_sorted,
+           Lattice L, double r2, float rc2, int rings, int min_neighbors, Owned own, double *__restrict__ entropy_sorted,
            MmeAcc *__restrict__ acc) {
   ThreadStats ts;
   ts.init();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = q_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < q_end; i += stride) {
     const P4 q = load_p4(S + i);
+    if (own.axis) {      // slab layout (dense table): halo points are neighbours only
+      int cx, cy, cz;
+      cell_from_tag(I, q.idx, 0, cx, cy, cz);
+      if (!owns(own, cy, cz)) continue;
+    }
     Moments m;
     m.init();
     walk_global(q, S, I, L, r2, rc2, rings, m);
@@ -184,6 +189,7 @@ struct MmeConst {
   double r2;                 // exact r^2
   int min_neighbors;
   int dimx, dimy, dimz;
+  Owned own;                 // slab layout: the planes whose points this rank evaluates (the halo points are neighbours only)
 };
 
 // squared gap (in cells) between a point at u in [0,1) of its cell and the cell d steps away on the same axis
@@ -211,6 +217,7 @@ mme_flat_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
     const int ix = (int)qr.w;
     const uint32_t cyz = SP ? cq : cq / (uint32_t)C.dimx;
     const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
+    if (!owns(C.own, iy, iz)) continue;
     const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
     float gl[R], gr[R];      // squared gaps to the d-th cell on the left / right along x (increasing in d)
 #pragma unroll
@@ -327,13 +334,14 @@ mme_rows_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long l
   const long long stride = (long long)gridDim.x * kRowsThreads;
   for (long long base = q_begin + blockIdx.x * (long long)kRowsThreads; base < q_end; base += stride) {
     const long long i = base + threadIdx.x;
-    const bool live = i < q_end;                      // dead lanes run along with empty runs (warp collectives need them)
-    const long long il = live ? i : q_end - 1;
+    const long long il = i < q_end ? i : q_end - 1;
     const float4 qr = __ldg(rel + il);
     const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(S + il) + 3)));
     const int ix = (int)qr.w;
     const uint32_t cyz = I.sparse ? cq : cq / (uint32_t)C.dimx;
-    const int iy = (int)(cyz % (uint32_t)C.dimy), iz = live ? (int)(cyz / (uint32_t)C.dimy) : -1000000;
+    const int iy = (int)(cyz % (uint32_t)C.dimy), izq = (int)(cyz / (uint32_t)C.dimy);
+    const bool live = i < q_end && owns(C.own, iy, izq);      // dead lanes run along with empty runs (warp collectives need them)
+    const int iz = live ? izq : -1000000;
     const float ux = qr.x * C.inv_h;
     {
       const float uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
@@ -458,6 +466,7 @@ mme_plane_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, long 
     const int ix = (int)qr.w;
     const uint32_t cyz = I.sparse ? cq : cq / (uint32_t)C.dimx;
     const int iy = (int)(cyz % (uint32_t)C.dimy), iz = (int)(cyz / (uint32_t)C.dimy);
+    if (!owns(C.own, iy, iz)) continue;
     const float ux = qr.x * C.inv_h, uy = qr.y * C.inv_h, uz = qr.z * C.inv_h;
     Moments m;
     m.init();
@@ -600,6 +609,8 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   const double rings_f = std::max(1.0, std::ceil(radius / c.lat.h - 1e-9));
   if (rings_f > 1.0e6) return fail(ctx, ME_ERR_RANGE, "nn_radius spans too many lattice cells");
   const int rings = (int)rings_f;
+  if (c.slab && rings > ctx->slab_halo)      // only with ME_MME_SHARED_LATTICE: the shared lattice keeps radius <= 3 cells
+    return fail(ctx, ME_ERR_RANGE, "nn_radius spans more lattice cells than the halo of the slab layout");
   const double rc = radius / c.lat.h;
   const float rc2 = (float)(rc * rc * (1.0 + 1e-5) + 1e-4);   // row pruning is conservative; the point test decides
   if (qe > qb) {
@@ -623,6 +634,7 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
       C.r2_hi = (float)((C.r2 + band) * (1.0 + 1e-7));
       C.min_neighbors = min_neighbors;
       C.dimx = c.lat.dims[0]; C.dimy = c.lat.dims[1]; C.dimz = c.lat.dims[2];
+      C.own = owned_of(c);
       // default: the run-table walk (4.45 ms on C3); ME_MME_KERNEL=rows selects the warp-synchronous row walk with deferred
       // accumulation (4.91 ms on C3: half of its issue slots idle while the longest run of a row finishes —
       // profiles/r02_kernel_variants.md)
@@ -640,7 +652,7 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
     } else {
       const int blocks = (int)std::min<long long>((qe - qb + kThreads - 1) / kThreads, (long long)ctx->sm_count * 64);
       mme_kernel<<<blocks, kThreads, 0, ctx->stream>>>(c.d_sorted, qb, qe, index_of(c), c.lat, radius * radius, rc2, rings,
-                                                      min_neighbors, c.d_entropy, acc);
+                                                      min_neighbors, owned_of(c), c.d_entropy, acc);
       ME_LAUNCH_CHECK(ctx);
     }
   }
@@ -662,7 +674,7 @@ int run_mme(me_ctx *ctx, int which, double radius, int min_neighbors, me_mme_acc
   if (c.grid_solo) {      // the solo lattice (and with it the sorted order of d_entropy) does not survive the next build
     ME_TRY(ensure(ctx, (void **)&c.d_entropy_caller, &c.cap_entropy_caller, c.n, sizeof(double)));
     const int blocks = (int)std::min<long long>((c.n + 255) / 256, (long long)ctx->sm_count * 16);
-    unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.n, c.d_entropy, c.d_entropy_caller);
+    unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.ns, c.d_entropy, c.d_entropy_caller);
     ME_LAUNCH_CHECK(ctx);
     c.entropy_caller_valid = true;
   }
@@ -680,7 +692,8 @@ int unsort_entropy(me_ctx *ctx, int which, double *h_entropy) {
   ME_TRY(ensure_work(ctx, (size_t)c.n * sizeof(double)));
   double *dst = (double *)ctx->d_work;
   int blocks = (int)std::min<long long>((c.n + 255) / 256, (long long)ctx->sm_count * 16);
-  unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.n, c.d_entropy, dst);
+  ME_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)c.n * sizeof(double), ctx->stream));      // slab mode: only this rank's points are written
+  unsort_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(c.d_sorted, c.ns, c.d_entropy, dst);
   ME_LAUNCH_CHECK(ctx);
   ME_CUDA(ctx, cudaMemcpyAsync(h_entropy, dst, (size_t)c.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

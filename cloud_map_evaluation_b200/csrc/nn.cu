@@ -36,7 +36,18 @@ struct NNConst {
   int want_full_cd;
   double max_d2;        // nothing beyond this squared distance matters (inf when full CD is wanted)
   double ref_maxabs;    // max |coordinate| of the reference cloud (slack of the face test)
+  // slab layout: only the planes [cov_lo, cov_hi) of the reference lattice along axis cov_axis (1: y, 2: z; 0: everything)
+  // are laid out on this rank
+  int cov_axis, cov_lo, cov_hi, cov_dim;
 };
+
+// distance (in cells) from lattice coordinate (uy, uz) to the nearest plane of the reference lattice that is NOT laid out on
+// this rank: beyond it the cloud is unknown, not empty
+__device__ __forceinline__ double cover_dist_cells(const NNConst &C, double uy, double uz) {
+  if (C.cov_axis == 0) return INFINITY;
+  const double ua = C.cov_axis == 1 ? uy : uz;
+  return fmin(C.cov_lo > 0 ? ua - (double)C.cov_lo : INFINITY, C.cov_hi < C.cov_dim ? (double)C.cov_hi - ua : INFINITY);
+}
 
 // device accumulator block: 8 x int64 then 13 x fp64 (see me_nn_accum)
 struct AccBlock {
@@ -168,8 +179,9 @@ __device__ __forceinline__ void finish_query(const P4 &q, uint32_t i, long long 
                                              double *__restrict__ nn_sq, uint32_t *__restrict__ far_list,
                                              unsigned int *__restrict__ far_count, double ux, double uy, double uz,
                                              double slack_h) {
-  const double g = fmin(fmin(face_dist_cells(ux, ix, 1, L.dims[0]), face_dist_cells(uy, iy, 1, L.dims[1])),
-                        face_dist_cells(uz, iz, 1, L.dims[2])) * L.h;
+  const double gcov = cover_dist_cells(C, uy, uz);
+  const double g = fmin(fmin(fmin(face_dist_cells(ux, ix, 1, L.dims[0]), face_dist_cells(uy, iy, 1, L.dims[1])),
+                             face_dist_cells(uz, iz, 1, L.dims[2])), gcov) * L.h;
   const double slack = slack_h * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
   const double ge = g - slack;
   const double ge2 = ge > 0 ? ge * ge : 0.0;
@@ -387,6 +399,7 @@ nn_tile_kernel(const P4 *__restrict__ Q, const uint32_t *__restrict__ q_off, Lat
 // ---------------------------------------------------------------------------------------------------------------
 struct FlatGeom {
   int qdimx, qdimy;            // query lattice (to decode the query's cell)
+  Owned own;                   // slab layout: the planes of the query lattice whose points this rank evaluates
   int q_sparse;                // the query cloud's tag holds the row id (sparse table) instead of the cell id
   int rdimx, rdimy, rdimz;     // reference lattice
   long long shx, shy, shz;     // reference cell = query cell + shift (the lattices share v and m)
@@ -412,6 +425,7 @@ nn_flat_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
     const P4 q = load_p4(Q + i);      // needed after the walk only; issued here so its latency hides behind the walk
     const uint32_t cq = cell_of(q.idx);
     const uint32_t cyz = G.q_sparse ? cq : cq / (uint32_t)G.qdimx;      // row id z * dimy + y of the query's own lattice
+    if (!owns(G.own, (int)(cyz % (uint32_t)G.qdimy), (int)(cyz / (uint32_t)G.qdimy))) continue;      // a halo point
     // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
     const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
                     cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
@@ -507,11 +521,11 @@ nn_rows_kernel(const P4 *__restrict__ Q, const float4 *__restrict__ qrel, long l
   const long long stride = (long long)gridDim.x * kFlatThreads;
   for (long long base = q_begin + blockIdx.x * (long long)kFlatThreads; base < q_end; base += stride) {
     const long long i = base + threadIdx.x;
-    const bool live = i < q_end;
-    const long long il = live ? i : q_end - 1;
+    const long long il = i < q_end ? i : q_end - 1;
     const float4 qr = __ldg(qrel + il);
     const uint32_t cq = cell_of(__double_as_longlong(__ldg(reinterpret_cast<const double *>(Q + il) + 3)));
     const uint32_t cyz = G.q_sparse ? cq : cq / (uint32_t)G.qdimx;
+    const bool live = i < q_end && owns(G.own, (int)(cyz % (uint32_t)G.qdimy), (int)(cyz / (uint32_t)G.qdimy));
     // the query's cell in reference-lattice coordinates (may lie outside the reference lattice)
     const long long cx = (long long)(int)qr.w + G.shx, cy = (long long)(cyz % (uint32_t)G.qdimy) + G.shy,
                     cz = (long long)(cyz / (uint32_t)G.qdimy) + G.shz;
@@ -605,7 +619,7 @@ __global__ void __launch_bounds__(kThreads)
 nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, Lattice L, CoarseGrid CG,
               NNConst C, int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2,
               const uint32_t *__restrict__ far_list, const unsigned int *__restrict__ far_count,
-              AccBlock *__restrict__ acc) {
+              uint32_t *__restrict__ unres_list, unsigned int *__restrict__ unres_count, AccBlock *__restrict__ acc) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -622,7 +636,8 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, L
     const double slack = 1e-9 * L.h + 1e-14 * (fabs(q.x) + fabs(q.y) + fabs(q.z) + C.ref_maxabs);
     double best = nn_d2[i];
     int bidx = nn_idx[i] >= 0 ? nn_idx[i] : 0x7fffffff;
-    bool beyond = false, done = false;
+    bool beyond = false, done = false, unresolved = false;
+    const double gcov = cover_dist_cells(C, uy, uz);
     auto warp_argmin = [&]() {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -632,13 +647,16 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, L
       }
     };
     // after a searched block whose faces are g cells away: resolved?  (sets done / beyond)
-    auto settle = [&](double g_cells) {
-      const double g = g_cells * L.h;
+    auto settle = [&](double g_block) {
+      const double g = fmin(g_block, gcov) * L.h;
       const double ge = g - slack;
       const double ge2 = ge > 0 ? ge * ge : 0.0;
       if (best < ge2) { done = true; return; }
       if (ge2 > C.max_d2) { beyond = best > C.max_d2; done = true; return; }
-      if (g == INFINITY) done = true;      // the block covers the whole lattice
+      if (g == INFINITY) { done = true; return; }      // the block covers the whole lattice
+      // the searched block has grown past the planes of this rank and the best still does not beat them: the answer may
+      // lie on another rank's planes — finished by brute force over the whole cloud (nn_brute_kernel)
+      if (g_block >= gcov) { unresolved = true; done = true; }
     };
     for (int r = 0; r <= fine_rings && !done; ++r) {
       const int side = 2 * r + 1;
@@ -723,11 +741,45 @@ nn_far_kernel(const P4 *__restrict__ Q, const P4 *__restrict__ R, CellIndex I, L
     }
     if (lane == 0) {
       atomicAdd(&acc->n_far, 1ull);
-      if (beyond || !(best < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; }
+      if (unresolved) unres_list[atomicAdd(unres_count, 1u)] = (uint32_t)i;
+      else if (beyond || !(best < INFINITY)) { nn_idx[i] = -1; nn_d2[i] = INFINITY; }
       else {
         nn_idx[i] = bidx;
         nn_d2[i] = best;      // the Eigen-order squared norm follows in nn_far_sq_kernel (needs the winner's coordinates)
       }
+    }
+  }
+}
+
+// slab mode, queries whose search left the planes of this rank: exact nearest neighbour over the WHOLE reference cloud (caller
+// order, resident on every rank) — one warp per query, lanes stride over the points.  Rare by construction (the halo is
+// several cells wide); correct for any count.
+__global__ void __launch_bounds__(kThreads)
+nn_brute_kernel(const P4 *__restrict__ Q, const double *__restrict__ ref_xyz, long long n_ref, NNConst C,
+                int32_t *__restrict__ nn_idx, double *__restrict__ nn_d2, const uint32_t *__restrict__ unres_list,
+                const unsigned int *__restrict__ unres_count) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned int nu = *unres_count;
+  for (long long w = warp; w < nu; w += nwarps) {
+    const long long i = unres_list[w];
+    const P4 q = load_p4(Q + i);
+    double best = INFINITY;
+    int bidx = 0x7fffffff;
+    for (long long j = lane; j < n_ref; j += 32) {
+      const double d2 = d2_kd(q.x, q.y, q.z, __ldg(ref_xyz + 3 * j), __ldg(ref_xyz + 3 * j + 1), __ldg(ref_xyz + 3 * j + 2));
+      if (d2 < best) { best = d2; bidx = (int)j; }      // j increases: the first (smallest) index of a tie is kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) {
+      if (!(best < INFINITY) || best > C.max_d2) { nn_idx[i] = -1; nn_d2[i] = INFINITY; }
+      else { nn_idx[i] = bidx; nn_d2[i] = best; }
     }
   }
 }
@@ -843,6 +895,9 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   C.accumulate = as_written ? 0 : 1;
   C.want_full_cd = p->want_full_cd ? 1 : 0;
   C.max_d2 = p->want_full_cd ? INFINITY : C.cutoff;
+  C.cov_axis = Rc.slab ? Rc.sl_axis : 0;
+  C.cov_lo = Rc.sc_lo; C.cov_hi = Rc.sc_hi;
+  C.cov_dim = Rc.slab ? Rc.lat.dims[Rc.sl_axis] : 0;
   C.ref_maxabs = 0;
   for (int a = 0; a < 3; ++a) C.ref_maxabs = std::max(C.ref_maxabs, std::max(std::fabs(Rc.bbox_min[a]), std::fabs(Rc.bbox_max[a])));
 
@@ -852,6 +907,8 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
                                         3 * Rc.max_cell_count >= (1 << 24));
   if (any_sparse && 3 * Rc.max_cell_count >= (1 << 24))
     return fail(ctx, ME_ERR_RANGE, "more than 2^24 / 3 points in one lattice cell of a sparse lattice");
+  if (use_tile && (Qc.slab || Rc.slab))
+    return fail(ctx, ME_ERR_RANGE, "the tile sweep cannot run on a slab layout (use ME_LAYOUT_REPLICATED for this data)");
   long long qb, qe, tb = 0, te = 0;
   ME_TRY(query_shard(ctx, qwhich, &qb, &qe));  // flat sweep: contiguous, cell-aligned range of the cell-sorted query order
   if (use_tile) {                              // (before the work buffer is carved up: the tile build scans in it)
@@ -862,11 +919,13 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_idx, &Qc.cap_nn, Qc.n, sizeof(int32_t)));
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_d2, &Qc.cap_nn_d2, Qc.n, sizeof(double)));
   ME_TRY(ensure(ctx, (void **)&Qc.d_nn_sq, &Qc.cap_nn_sq, Qc.n, sizeof(double)));
-  // work buffer: far list (n uint32) after a 256-byte header holding the far counter and the query counter
-  ME_TRY(ensure_work(ctx, 256 + (size_t)Qc.n * sizeof(uint32_t)));
+  // work buffer: far list and unresolved list (n uint32 each) after a 256-byte header holding the counters
+  ME_TRY(ensure_work(ctx, 256 + 2 * (size_t)Qc.n * sizeof(uint32_t)));
   unsigned int *far_count = (unsigned int *)ctx->d_work;
   unsigned long long *n_eval = (unsigned long long *)((char *)ctx->d_work + 64);
+  unsigned int *unres_count = (unsigned int *)((char *)ctx->d_work + 128);
   uint32_t *far_list = (uint32_t *)((char *)ctx->d_work + 256);
+  uint32_t *unres_list = far_list + Qc.n;
   AccBlock *acc = (AccBlock *)ctx->d_scratch;
   ME_CUDA(ctx, cudaMemsetAsync(acc, 0, sizeof(AccBlock), ctx->stream));
   ME_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, 256, ctx->stream));
@@ -890,6 +949,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       FlatGeom G;
       G.qdimx = Qc.lat.dims[0]; G.qdimy = Qc.lat.dims[1];
       G.q_sparse = Qc.lat.sparse;
+      G.own = owned_of(Qc);
       G.rdimx = Rc.lat.dims[0]; G.rdimy = Rc.lat.dims[1]; G.rdimz = Rc.lat.dims[2];
       G.shx = (long long)(Qc.lat.k_lo[0] - Rc.lat.k_lo[0]) * Qc.lat.m;
       G.shy = (long long)(Qc.lat.k_lo[1] - Rc.lat.k_lo[1]) * Qc.lat.m;
@@ -919,8 +979,13 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     }
     ME_LAUNCH_CHECK(ctx);
     nn_far_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_sorted, index_of(Rc), Rc.lat, coarse_of(Rc), C,
-                                                                  Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, acc);
+                                                                  Qc.d_nn_idx, Qc.d_nn_d2, far_list, far_count, unres_list, unres_count, acc);
     ME_LAUNCH_CHECK(ctx);
+    if (Rc.slab) {
+      nn_brute_kernel<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_xyz, Rc.n, C, Qc.d_nn_idx, Qc.d_nn_d2,
+                                                                      unres_list, unres_count);
+      ME_LAUNCH_CHECK(ctx);
+    }
     if (C.accumulate) {
       nn_far_sq_kernel<<<ctx->sm_count, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Rc.d_xyz, Qc.d_nn_idx, Qc.d_nn_sq, far_list,
                                                                     far_count);
@@ -933,7 +998,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
       ME_LAUNCH_CHECK(ctx);
     }
     if (as_written) {
-      pair_as_written_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.n, Qc.d_nn_idx, Qc.d_nn_d2,
+      pair_as_written_kernel<<<fill_blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.ns, Qc.d_nn_idx, Qc.d_nn_d2,
                                                                        Qc.d_xyz, Qc.n, Rc.d_xyz, Rc.n, C, acc);
       ME_LAUNCH_CHECK(ctx);
     }
@@ -943,7 +1008,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
     ME_LAUNCH_CHECK(ctx);
   }
   if (to_block) {      // the accumulators stay on the device (all-reduced there, fetched once per pass)
-    pack_nn_kernel<<<1, 32, 0, ctx->stream>>>(acc, (sharded && use_tile) ? n_eval : nullptr, sharded ? qe - qb : Qc.n,
+    pack_nn_kernel<<<1, 32, 0, ctx->stream>>>(acc, (sharded && use_tile) ? n_eval : nullptr, Qc.slab ? Qc.n_owned : (sharded ? qe - qb : Qc.n),
                                               ctx->d_block + (qwhich == ME_CLOUD_EST ? 0 : kBlkNN));
     ME_LAUNCH_CHECK(ctx);
     Qc.nn_valid = true;
@@ -955,7 +1020,7 @@ static int run_direction(me_ctx *ctx, int qwhich, const me_nn_params *p, me_nn_a
   if (sharded && use_tile) ME_CUDA(ctx, cudaMemcpyAsync(h_eval, n_eval, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::memset(out, 0, sizeof(*out));
-  out->n_query = !sharded ? Qc.n : (use_tile ? (int64_t)*h_eval : qe - qb);
+  out->n_query = !sharded ? Qc.n : (use_tile ? (int64_t)*h_eval : (Qc.slab ? Qc.n_owned : qe - qb));
   out->n_corr = (int64_t)h->n_corr;
   for (int k = 0; k < 5; ++k) { out->n_inlier[k] = (int64_t)h->n_inl[k]; out->sum_d[k] = h->sum_d[k]; out->sum_d2[k] = h->sum_d2[k]; }
   out->n_ub = (int64_t)h->n_ub;
@@ -997,7 +1062,7 @@ int unsort_nn(me_ctx *ctx, int which_query, int32_t *h_idx, double *h_d2) {
   int blocks = (int)std::min<long long>((Qc.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
   fill_nn_kernel<<<blocks, kThreads, 0, ctx->stream>>>(oidx, od2, Qc.n);
   ME_LAUNCH_CHECK(ctx);
-  unsort_nn_kernel<<<blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.n, Qc.d_nn_idx, Qc.d_nn_d2, oidx, od2);
+  unsort_nn_kernel<<<blocks, kThreads, 0, ctx->stream>>>(Qc.d_sorted, Qc.ns, Qc.d_nn_idx, Qc.d_nn_d2, oidx, od2);
   ME_LAUNCH_CHECK(ctx);
   if (h_idx) ME_CUDA(ctx, cudaMemcpyAsync(h_idx, oidx, (size_t)Qc.n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (h_d2) ME_CUDA(ctx, cudaMemcpyAsync(h_d2, od2, (size_t)Qc.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

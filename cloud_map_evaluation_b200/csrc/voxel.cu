@@ -39,7 +39,7 @@ voxel_precount_kernel(const P4 *__restrict__ S, const float4 *__restrict__ rel, 
 }
 
 __global__ void __launch_bounds__(kThreads)
-voxel_moments_kernel(const P4 *__restrict__ S, CellIndex I, Lattice L, int precounted,
+voxel_moments_kernel(const P4 *__restrict__ S, CellIndex I, Lattice L, int precounted, Owned vown,
                      int32_t *__restrict__ cnt, double *__restrict__ mom, unsigned long long *__restrict__ n_occupied) {
   const int sub = threadIdx.x & 15;
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 4;
@@ -53,10 +53,11 @@ voxel_moments_kernel(const P4 *__restrict__ S, CellIndex I, Lattice L, int preco
     const bool live = vox < L.nvoxels;
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int n = 0;
-    if (live && !(precounted && cnt[vox] == 0)) {
-      const int vx = (int)(vox % L.nvox[0]);
-      const int vy = (int)((vox / L.nvox[0]) % L.nvox[1]);
-      const int vz = (int)(vox / ((long long)L.nvox[0] * L.nvox[1]));
+    const int vx = (int)(vox % L.nvox[0]);
+    const int vy = (int)((vox / L.nvox[0]) % L.nvox[1]);
+    const int vz = (int)(vox / ((long long)L.nvox[0] * L.nvox[1]));
+    // slab layout: a voxel layer has one owner; the voxels of other ranks stay empty here (their W arrives by all-reduce)
+    if (live && owns(vown, vy, vz) && !(precounted && cnt[vox] == 0)) {
       const double cx = ((double)(L.k_lo[0] + vx) + 0.5) * L.v, cy = ((double)(L.k_lo[1] + vy) + 0.5) * L.v,
                    cz = ((double)(L.k_lo[2] + vz) + 0.5) * L.v;
       for (int t = sub; t < m * m; t += 16) {
@@ -238,13 +239,13 @@ struct AwdAcc {
 // ---- pairing + Wasserstein: one thread per est voxel -----------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 awd_kernel(Lattice Le, Lattice Lg, const int32_t *__restrict__ cnt_e, const double *__restrict__ mom_e,
-           const int32_t *__restrict__ cnt_g, const double *__restrict__ mom_g, int min_points,
+           const int32_t *__restrict__ cnt_g, const double *__restrict__ mom_g, int min_points, double missing,
            double *__restrict__ w_out, uint32_t *__restrict__ pair_list, double *__restrict__ rows27,
            AwdAcc *__restrict__ acc) {
   unsigned long long l_active = 0, l_new = 0;
   for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < Le.nvoxels;
        vox += (long long)gridDim.x * blockDim.x) {
-    double w = NAN;
+    double w = missing;      // NaN, or -1 when the table is MAX-all-reduced across ranks (slab layout)
     const int ne = cnt_e[vox];
     if (ne > 0) {
       const int vx = (int)(vox % Le.nvox[0]);
@@ -322,7 +323,8 @@ scs_kernel(Lattice Le, const double *__restrict__ w_vox, const uint32_t *__restr
       if (dx == 0 && dy == 0 && dz == 0) return NAN;
       const int x = vx + dx, y = vy + dy, z = vz + dz;
       if (x < 0 || x >= Le.nvox[0] || y < 0 || y >= Le.nvox[1] || z < 0 || z >= Le.nvox[2]) return NAN;
-      return __ldg(w_vox + ((long long)z * Le.nvox[1] + y) * Le.nvox[0] + x);
+      const double w = __ldg(w_vox + ((long long)z * Le.nvox[1] + y) * Le.nvox[0] + x);
+      return w < 0.0 ? NAN : w;      // -1: no pair in that voxel (the all-reducible encoding)
     };
     if (cached) {
 #pragma unroll
@@ -361,13 +363,21 @@ __global__ void zero_awd_acc_kernel(AwdAcc *a, unsigned long long *occ2) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
-            double **rows27) {
-  std::memset(out, 0, sizeof(*out));
-  if (n_rows) *n_rows = 0;
-  if (rows27) *rows27 = nullptr;
+// The stage in two halves.  voxel_begin: lattices, per-voxel moments, pairing + Wasserstein distances (the W table over the
+// estimated cloud's voxels stays in the work buffer).  voxel_scs: the SCS sweep over the paired voxels of this rank.  On a
+// slab layout every rank computes the voxel layers it owns and the caller MAX-all-reduces the W table between the halves
+// (SCS reads the 11^3 neighbourhood of a voxel, map_eval.cpp:353); all eight counters / sums are then SUM-reducible.
+// ---------------------------------------------------------------------------------------------------------------
+static Owned voxel_owned(const Cloud &c) {
+  Owned o;
+  o.axis = c.slab ? c.sl_axis : 0;
+  o.lo = c.so_lo / std::max(1, c.lat.m); o.hi = c.so_hi / std::max(1, c.lat.m);      // slab planes are whole voxel layers
+  return o;
+}
+
+static int voxel_begin_impl(me_ctx *ctx, double voxel_size, int min_points, bool want_rows, double **d_rows_out) {
+  ctx->vox_open = false;
   if (!(voxel_size > 0)) return fail(ctx, ME_ERR_INVALID, "vmd_voxel_size must be > 0");
-  if (scs_radius < 0 || scs_radius > 64) return fail(ctx, ME_ERR_INVALID, "scs_radius out of range");
   if (ctx->cloud[0].n <= 0 || ctx->cloud[1].n <= 0) return fail(ctx, ME_ERR_EMPTY, "both clouds must be set");
   // the lattices must be aligned with this voxel size; rebuild them if they are not
   for (int w = 0; w < 2; ++w) {
@@ -380,6 +390,9 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
   const Lattice Le = E.lat, Lg = G.lat;
   if (Le.nvoxels < 0 || Lg.nvoxels < 0 || Le.nvoxels >= 0x7fffffffll || Lg.nvoxels >= 0x7fffffffll)
     return fail(ctx, ME_ERR_RANGE, "vmd_voxel_size is too small for the extent of the clouds: the voxel tables are dense (2^31 voxels at most)");
+  const bool slab = E.slab || G.slab;
+  if (slab && want_rows)
+    return fail(ctx, ME_ERR_INVALID, "the per-voxel rows are not available on a slab layout (every rank holds its own voxels only)");
 
   // work layout: cnt_e | cnt_g | mom_e | mom_g | w_vox | pair_list | rows27
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -392,14 +405,15 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
   size_t o_rows = o_pairs + align((size_t)Le.nvoxels * sizeof(uint32_t));
   // a voxel pair needs >= min_points points in each cloud, which bounds the number of rows
   long long max_pairs = std::min<long long>(Le.nvoxels, std::min(E.n, G.n) / std::max(1, min_points) + 1);
-  size_t total = o_rows + (rows27 ? align((size_t)max_pairs * 27 * sizeof(double)) : 0);
+  size_t total = o_rows + (want_rows ? align((size_t)max_pairs * 27 * sizeof(double)) : 0);
   ME_TRY(ensure_work(ctx, total));
   char *base = (char *)ctx->d_work;
   int32_t *cnt_e = (int32_t *)(base + o_cnt_e), *cnt_g = (int32_t *)(base + o_cnt_g);
   double *mom_e = (double *)(base + o_mom_e), *mom_g = (double *)(base + o_mom_g);
   double *w_vox = (double *)(base + o_w);
   uint32_t *pair_list = (uint32_t *)(base + o_pairs);
-  double *d_rows = rows27 ? (double *)(base + o_rows) : nullptr;
+  double *d_rows = want_rows ? (double *)(base + o_rows) : nullptr;
+  if (d_rows_out) *d_rows_out = d_rows;
 
   AwdAcc *acc = (AwdAcc *)ctx->d_scratch;
   unsigned long long *occ = (unsigned long long *)((char *)ctx->d_scratch + 256);
@@ -412,33 +426,87 @@ int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_a
     const int pb_g = (int)std::min<long long>((G.n + kThreads - 1) / kThreads, (long long)ctx->sm_count * 16);
     if (Le.sparse) {
       ME_CUDA(ctx, cudaMemsetAsync(cnt_e, 0, (size_t)Le.nvoxels * sizeof(int32_t), ctx->stream));
-      voxel_precount_kernel<<<pb_e, kThreads, 0, ctx->stream>>>(E.d_sorted, E.d_rel, E.n, index_of(E), Le, cnt_e);
+      voxel_precount_kernel<<<pb_e, kThreads, 0, ctx->stream>>>(E.d_sorted, E.d_rel, E.ns, index_of(E), Le, cnt_e);
       ME_LAUNCH_CHECK(ctx);
     }
     if (Lg.sparse) {
       ME_CUDA(ctx, cudaMemsetAsync(cnt_g, 0, (size_t)Lg.nvoxels * sizeof(int32_t), ctx->stream));
-      voxel_precount_kernel<<<pb_g, kThreads, 0, ctx->stream>>>(G.d_sorted, G.d_rel, G.n, index_of(G), Lg, cnt_g);
+      voxel_precount_kernel<<<pb_g, kThreads, 0, ctx->stream>>>(G.d_sorted, G.d_rel, G.ns, index_of(G), Lg, cnt_g);
       ME_LAUNCH_CHECK(ctx);
     }
-    voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, index_of(E), Le, Le.sparse, cnt_e, mom_e, occ);
+    voxel_moments_kernel<<<std::max(1, blocks_e), kThreads, 0, ctx->stream>>>(E.d_sorted, index_of(E), Le, Le.sparse, voxel_owned(E), cnt_e, mom_e, occ);
     ME_LAUNCH_CHECK(ctx);
     int blocks_g = (int)std::min<long long>((Lg.nvoxels * 16 + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
-    voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, index_of(G), Lg, Lg.sparse, cnt_g, mom_g, occ + 1);
+    voxel_moments_kernel<<<std::max(1, blocks_g), kThreads, 0, ctx->stream>>>(G.d_sorted, index_of(G), Lg, Lg.sparse, voxel_owned(G), cnt_g, mom_g, occ + 1);
     ME_LAUNCH_CHECK(ctx);
   }
   {
     StageTimer timer(ctx, 7);
     int blocks = (int)std::min<long long>((Le.nvoxels + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8);
-    awd_kernel<<<std::max(1, blocks), kThreads, 0, ctx->stream>>>(Le, Lg, cnt_e, mom_e, cnt_g, mom_g, min_points, w_vox,
-                                                                 pair_list, d_rows, acc);
+    awd_kernel<<<std::max(1, blocks), kThreads, 0, ctx->stream>>>(Le, Lg, cnt_e, mom_e, cnt_g, mom_g, min_points, slab ? -1.0 : (double)NAN,
+                                                                 w_vox, pair_list, d_rows, acc);
     ME_LAUNCH_CHECK(ctx);
   }
-  {
-    StageTimer timer(ctx, 8);
-    if (scs_radius == 5) scs_kernel<5><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
-    else scs_kernel<0><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
-    ME_LAUNCH_CHECK(ctx);
+  ctx->vox_open = true;
+  ctx->vox_nvox = Le.nvoxels;
+  ctx->vox_o_w = o_w;
+  ctx->vox_o_pairs = o_pairs;
+  return ME_OK;
+}
+
+static int voxel_scs_impl(me_ctx *ctx, int scs_radius) {
+  if (!ctx->vox_open) return fail(ctx, ME_ERR_INVALID, "me_voxel_finish before me_voxel_begin");
+  if (scs_radius < 0 || scs_radius > 64) return fail(ctx, ME_ERR_INVALID, "scs_radius out of range");
+  ctx->vox_open = false;
+  const Lattice Le = ctx->cloud[ME_CLOUD_EST].lat;
+  const double *w_vox = (const double *)((char *)ctx->d_work + ctx->vox_o_w);
+  const uint32_t *pair_list = (const uint32_t *)((char *)ctx->d_work + ctx->vox_o_pairs);
+  AwdAcc *acc = (AwdAcc *)ctx->d_scratch;
+  StageTimer timer(ctx, 8);
+  if (scs_radius == 5) scs_kernel<5><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
+  else scs_kernel<0><<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(Le, w_vox, pair_list, scs_radius, acc);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
+int voxel_begin(me_ctx *ctx, double voxel_size, int min_points) { return voxel_begin_impl(ctx, voxel_size, min_points, false, nullptr); }
+
+int voxel_w_table(me_ctx *ctx, double **d_w, int64_t *n) {
+  if (!ctx->vox_open) return fail(ctx, ME_ERR_INVALID, "me_voxel_w_table before me_voxel_begin");
+  *d_w = (double *)((char *)ctx->d_work + ctx->vox_o_w);
+  *n = (int64_t)ctx->vox_nvox;
+  return ME_OK;
+}
+
+// the eight SUM-reducible values of the stage -> the context's accumulator block
+__global__ void pack_awd_kernel(const AwdAcc *__restrict__ a, const unsigned long long *__restrict__ occ, double *__restrict__ blk) {
+  if (threadIdx.x != 0) return;
+  blk[0] = (double)a->n_pairs; blk[1] = (double)a->n_scs; blk[2] = (double)occ[0]; blk[3] = (double)occ[1];
+  blk[4] = (double)a->n_active; blk[5] = (double)a->n_new; blk[6] = a->sum_w; blk[7] = a->sum_scs;
+}
+
+int voxel_finish_block(me_ctx *ctx, int scs_radius) {
+  ME_TRY(voxel_scs_impl(ctx, scs_radius));
+  pack_awd_kernel<<<1, 32, 0, ctx->stream>>>((const AwdAcc *)ctx->d_scratch, (const unsigned long long *)((char *)ctx->d_scratch + 256),
+                                            ctx->d_block + kBlkAwd);
+  ME_LAUNCH_CHECK(ctx);
+  return ME_OK;
+}
+
+int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
+            double **rows27) {
+  std::memset(out, 0, sizeof(*out));
+  if (n_rows) *n_rows = 0;
+  if (rows27) *rows27 = nullptr;
+  if (scs_radius < 0 || scs_radius > 64) return fail(ctx, ME_ERR_INVALID, "scs_radius out of range");
+  double *d_rows = nullptr;
+  ME_TRY(voxel_begin_impl(ctx, voxel_size, min_points, rows27 != nullptr, &d_rows));
+  if (ctx->cloud[ME_CLOUD_EST].slab || ctx->cloud[ME_CLOUD_GT].slab) {
+    ctx->vox_open = false;
+    return fail(ctx, ME_ERR_INVALID, "slab layout: run the voxel stage as me_voxel_begin / all-reduce of me_voxel_w_table / "
+                                     "me_voxel_finish_accum_device");
   }
+  ME_TRY(voxel_scs_impl(ctx, scs_radius));
   struct Host { AwdAcc a; char pad[256 - sizeof(AwdAcc)]; unsigned long long occ[2]; };
   Host *h = (Host *)ctx->h_pinned;
   ME_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch, sizeof(Host), cudaMemcpyDeviceToHost, ctx->stream));

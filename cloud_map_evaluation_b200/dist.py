@@ -90,3 +90,14 @@ def allreduce_block(ctx, device, group=None):
     t = torch.as_tensor(_DeviceBlock(ptr, n_sum + n_max), device=device)
     dist.all_reduce(t[:n_sum], group=group)
     dist.all_reduce(t[n_sum:], op=dist.ReduceOp.MAX, group=group)
+
+
+def allreduce_voxel_w(ctx, device, group=None):
+    """Slab layout, between MapEvalB200.voxel_begin and voxel_finish_accum_device: MAX-all-reduce of the W table over the
+    estimated cloud's voxels in place (-1 = no pair; every voxel has one owner), so that the SCS sweep of every rank sees
+    the W of the neighbouring ranks' voxels."""
+    import torch
+    import torch.distributed as dist
+    ptr, n = ctx.voxel_w_table()
+    if n > 0:
+        dist.all_reduce(torch.as_tensor(_DeviceBlock(ptr, n), device=device), op=dist.ReduceOp.MAX, group=group)

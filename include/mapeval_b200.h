@@ -162,6 +162,21 @@ ME_API void me_destroy(me_ctx *ctx);
 ME_API const char *me_last_error(const me_ctx *ctx);      /* ctx may be NULL: last error of me_create on this thread */
 ME_API int  me_set_stream(me_ctx *ctx, void *cuda_stream);
 ME_API int  me_set_shard(me_ctx *ctx, int32_t rank, int32_t world);
+/* How a context of a multi-GPU job (world > 1) lays the clouds out.  ME_LAYOUT_REPLICATED (default): both whole clouds on
+ * every rank, the query ranges of the sweeps sharded.  ME_LAYOUT_SLAB: every rank lays out only the voxel layers it owns
+ * along y or z (whichever balances), plus a halo of four lattice cells, of BOTH clouds, and evaluates the points of its
+ * layers — the lattice builds and the voxel stage shard with the sweeps.  The clouds themselves stay replicated (caller
+ * order, set with me_set_cloud*): searches that leave the halo are finished exactly over the whole cloud.  The partial
+ * accumulators are reduced as before (me_accum_block); the voxel stage runs as me_voxel_begin / all-reduce(MAX) of
+ * me_voxel_w_table / me_voxel_finish_accum_device.  A scene that cannot be cut (sparse cell table, fewer than 2 x world voxel
+ * layers, one rank holding > 75 %) silently stays replicated — me_layout_active tells.  me_eval_awd, the tile sweep and
+ * per-point outputs of other ranks' points are not available on an active slab layout. */
+#define ME_LAYOUT_REPLICATED 0
+#define ME_LAYOUT_SLAB 1
+ME_API int  me_set_layout(me_ctx *ctx, int32_t layout);
+/* after the lattices were built (any sweep): *layout = the layout in force, *axis = 1 (y) / 2 (z) / 0, n_laid_out[2] = the
+ * points of (est, gt) this rank laid out, n_owned[2] = the points it evaluates.  Any pointer may be NULL. */
+ME_API int  me_layout_active(me_ctx *ctx, int32_t *layout, int32_t *axis, int64_t n_laid_out[2], int64_t n_owned[2]);
 ME_API int  me_synchronize(me_ctx *ctx);
 
 /* replaces: io::ReadPointCloud* results held in map_3d_/gt_3d_ (map_eval.cpp:10-21) — the clouds the path reads.
@@ -236,11 +251,22 @@ ME_API int  me_eval_mme_accum_device(me_ctx *ctx, int which, double radius, int3
 ME_API int  me_accum_block(me_ctx *ctx, double **device_block, int32_t *n_sum, int32_t *n_max);
 ME_API int  me_accum_fetch(me_ctx *ctx, me_nn_accum *est_to_gt, me_nn_accum *gt_to_est, me_mme_accum *mme_est,
                            me_mme_accum *mme_gt);
+/* The voxel stage (calculateVMD, map_eval.cpp:240-390) in two halves, for either layout.  me_voxel_begin: lattices,
+ * per-voxel Gaussians, pairing and Wasserstein distances of the voxels this rank owns (all of them on a replicated layout).
+ * me_voxel_w_table: DEVICE address and length of the W table over the estimated cloud's voxels (-1 = no pair) — on an
+ * active slab layout the caller MAX-all-reduces it in place, so that every rank sees the W of its neighbours' voxels (SCS
+ * reads 11^3 voxels around each pair, map_eval.cpp:353).  me_voxel_finish_accum_device: the SCS sweep over this rank's
+ * pairs; leaves the stage's eight SUM-reducible values in the accumulator block.  me_accum_fetch_awd: after the block's
+ * all-reduce, AWD / SCS / the voxel counts (map_eval.cpp:324-325,387) from the block. */
+ME_API int  me_voxel_begin(me_ctx *ctx, double voxel_size, int32_t min_points);
+ME_API int  me_voxel_w_table(me_ctx *ctx, double **device_w, int64_t *n);
+ME_API int  me_voxel_finish_accum_device(me_ctx *ctx, int32_t scs_radius);
+ME_API int  me_accum_fetch_awd(me_ctx *ctx, me_awd_result *out);
 
 /* replaces: MapEval::calculateVMD (map_eval.cpp:240-390) with VoxelCalculator::buildVoxelMap / computeVoxelEntropy /
  * updateVoxelMap / computeWassersteinDistanceGaussian / getNeighborIndices (voxel_calculator.cpp:7-56,97-172,241-245).
  * rows27 (nullable): library-allocated n_rows x 27 table = the columns of voxel_errors.txt (map_eval.cpp:292-302),
- * release with me_free.  Not sharded: every rank computes the whole (cheap) voxel stage. */
+ * release with me_free.  Replicated layout only: every rank computes the whole voxel stage (me_voxel_* shards it). */
 ME_API int  me_eval_awd(me_ctx *ctx, double voxel_size, int32_t min_points, int32_t scs_radius, me_awd_result *out,
                  int64_t *n_rows, double **rows27);
 /* The voxel-pair half of calculateVMD on GIVEN voxel Gaussians: rows27 = n_rows x 27 in the column layout of

@@ -515,7 +515,7 @@ def test_device_resident_accumulators_equal_the_host_path(api, O):
         ctx.eval_mme_accum_device(A.ME_CLOUD_GT, cfg["nn_radius"], 5)
         ctx.eval_nn_accum_device(p)
         ptr, n_sum, n_max = ctx.accum_block()
-        assert ptr and n_sum == 50 and n_max == 4
+        assert ptr and n_sum == 58 and n_max == 4
         e2, g2, (m_e2, m_g2) = ctx.accum_fetch(want_mme=(True, True))
     for a, b in ((e, e2), (g, g2)):
         da, db = A.struct_to_dict(a), A.struct_to_dict(b)
