@@ -6,6 +6,7 @@
 // map_eval.cpp:1213-1214,1226-1227,1401-1402,1448-1449,1550-1551,1618-1619) and its std::unordered_map voxel
 // hashing (voxel_calculator.cpp:21-56).  All kernels here are HBM-streaming integer/byte work: coalesced loads,
 // grids sized in multiples of the SM count, no tensor cores.
+#include <cstdio>
 #include "common.cuh"
 #include <algorithm>
 #include <climits>
@@ -758,6 +759,9 @@ static int plan_slabs(me_ctx *ctx, Cloud &c, const Lattice &L) {
     const double share = (double)worst / (double)total;
     if (share < best_share) { best_share = share; best_b = b; best_axis = axis; }
   }
+  if (getenv("ME_DEBUG_SLAB"))
+    fprintf(stderr, "[mapeval] slab plan: rank %d/%d lattice %d x %d x %d (m = %d), axis %d, busiest share %.3f\n", ctx->rank, W,
+            L.dims[0], L.dims[1], L.dims[2], L.m, best_axis, best_share);
   // worth it only if the busiest rank lays out clearly less than the whole cloud
   if (best_axis == 0 || best_share > 0.75) return ME_OK;
   const int r = ctx->rank;
@@ -876,6 +880,7 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     }
   } else if (built && !solo && slab_wanted(ctx)) {
     // a sparse lattice is laid out whole: the pass falls back to replicated lattices (the other cloud is laid out again)
+    if (getenv("ME_DEBUG_SLAB")) fprintf(stderr, "[mapeval] slab plan: rank %d sparse cell table, replicated layout\n", ctx->rank);
     ctx->slab_planned = true;
     if (ctx->slab_on) {
       ctx->slab_on = false;

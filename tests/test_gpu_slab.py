@@ -142,7 +142,10 @@ def _cmp_job(job, ref, n_est, n_gt, world):
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_flat_outdoor_scene_is_cut_along_y(api, world):
+def test_flat_outdoor_scene_is_cut_along_y(api, world, monkeypatch):
+    # at this scale the scene would get the sparse cell table, which is laid out whole (replicated); the full-size C3 / C5
+    # lattices are dense
+    monkeypatch.setenv("ME_NO_SPARSE", "1")
     est, gt, cfg = synth.make_pair("C3", scale=0.04)
     p = A.make_nn_params(cfg["tau"], 1.0)
     ref = _reference(api, est, gt, p, cfg["nn_radius"], cfg["vmd_voxel_size"], 20)
@@ -175,10 +178,11 @@ def test_indoor_rooms_small_radius(api, world):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-def test_neighbours_on_other_ranks_slabs(api, world):
+def test_neighbours_on_other_ranks_slabs(api, world, monkeypatch):
     """The ground truth covers only the south half of the scene, the estimate all of it (plus far outliers): the nearest
     neighbour of most northern points lies tens of metres away, on another rank's slab — found by the exact finish over the
     whole cloud; full Chamfer and the gt -> est direction see them."""
+    monkeypatch.setenv("ME_NO_SPARSE", "1")
     est, gt, cfg = synth.make_pair("C3", scale=0.02)
     gt = np.ascontiguousarray(gt[gt[:, 1] < 90.0])
     rs = np.random.RandomState(5)
@@ -215,7 +219,7 @@ def test_scene_that_cannot_be_cut_stays_replicated(api):
 
 
 def test_one_call_voxel_stage_refuses_an_active_slab_layout(api):
-    est, gt, cfg = synth.make_pair("C3", scale=0.02)
+    est, gt, cfg = synth.make_pair("C5", scale=0.001)
     with api.MapEvalB200(rank=1, world=2, vmd_voxel_size=cfg["vmd_voxel_size"]) as ctx:
         ctx.set_layout(A.ME_LAYOUT_SLAB)
         ctx.set_cloud(EST, est)
@@ -227,3 +231,21 @@ def test_one_call_voxel_stage_refuses_an_active_slab_layout(api):
         # back to the replicated layout: the same context serves the one-call stage again
         ctx.set_layout(A.ME_LAYOUT_REPLICATED)
         assert ctx.calculateVMD(cfg["vmd_voxel_size"], 20, 5).n_voxels_est > 0
+
+
+def test_sparse_cell_table_stays_replicated(api):
+    """A scene that gets the sparse cell table (laid out whole) ignores the slab request: same results, replicated layout."""
+    est, gt, cfg = synth.make_pair("C3", scale=0.02)
+    p = A.make_nn_params(cfg["tau"], 1.0)
+    ref = _reference(api, est, gt, p, cfg["nn_radius"], cfg["vmd_voxel_size"], 20)
+    tot = 0
+    for r in range(2):
+        with api.MapEvalB200(rank=r, world=2, vmd_voxel_size=cfg["vmd_voxel_size"]) as ctx:
+            ctx.set_layout(A.ME_LAYOUT_SLAB)
+            ctx.set_cloud(EST, est)
+            ctx.set_cloud(GT, gt)
+            e, g = ctx.eval_nn_accum(p)
+            if ctx.layout_active()["layout"] != A.ME_LAYOUT_REPLICATED:
+                pytest.skip("this scene got a dense table")
+            tot += e.n_inlier[0]
+    assert tot == ref["e"].n_inlier[0]
