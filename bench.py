@@ -426,6 +426,9 @@ def main():
                        "n_gt": n_gt, "tau": cfg["tau"], "icp_max_distance": 1.0, "nn_radius": cfg["nn_radius"],
                        "vmd_voxel_size": cfg["vmd_voxel_size"], "mme_gt": bool(cfg["gt_mme"]),
                        "generated": gen,
+                       "planning": "the context remembers the lattice plan (refined cell edge, slab cut) of a cloud pair: passes "
+                                   "after the first plan in one step instead of 2-3 histogram passes; the lattices themselves "
+                                   "are rebuilt from the points every pass",
                        "parallelism": (f"slab layout x{world}: voxel layers along {'xyz'[lay.get('axis', 0)]} owned per rank, lattice builds, "
                                        f"sweeps and voxel stage sharded; rank 0 lays out {lay['n_laid_out'][0]} + {lay['n_laid_out'][1]} "
                                        f"points and evaluates {lay['n_owned'][0]} + {lay['n_owned'][1]}") if slab else

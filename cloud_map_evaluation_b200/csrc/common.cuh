@@ -119,6 +119,27 @@ struct Cloud {
   bool normal_valid = false;
 };
 
+// Lattice planning is data dependent (the cell edge is refined on the measured occupancy; the slabs are cut on the layer
+// histogram) and costs extra histogram passes and host round trips.  The outcome for one (cloud, other cloud, settings)
+// constellation is remembered: evaluating a cloud pair of the same sizes and bounding boxes again — repeated passes over the
+// same maps — re-uses it.  The plan only steers performance; results do not depend on it.
+struct PlanCache {
+  bool valid = false;
+  // key
+  long long n = 0, other_n = -1;
+  double bmin[3], bmax[3], obmin[3], obmax[3];
+  double v_req = 0, nn_cell = 0;
+  long long budget = 0;
+  bool sp = false, slab_request = false;
+  int rank = 0, world = 1;
+  // value
+  double h_target = 0;
+  Lattice lat;
+  bool slab_planned = false, slab_on = false;
+  int slab_axis = 0;
+  long long slab_k0 = 0, slab_k1 = 0;
+};
+
 }  // namespace me
 
 struct me_ctx {
@@ -136,6 +157,7 @@ struct me_ctx {
   int slab_axis = 0;                       // 1: y, 2: z
   long long slab_k0 = 0, slab_k1 = 0;      // owned world voxel layers [k0, k1) along slab_axis (LLONG_MIN/4, LLONG_MAX/4 at the ends)
   int slab_halo = 4;                       // cells; covers the 3 rings of an MME sweep on the shared lattice
+  me::PlanCache plan_cache[2];
   // voxel stage split in two (me_voxel_begin / me_voxel_finish_accum_device): state kept between the halves
   bool vox_open = false;
   long long vox_nvox = 0;

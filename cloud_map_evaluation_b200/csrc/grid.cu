@@ -829,7 +829,18 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     ctx->slab_planned = false;              // the slabs are planned again with the spec
     const Cloud *other = (o.n > 0 && o.bbox_valid) ? &o : nullptr;
     double h_target = ctx->nn_cell_size > 0 ? ctx->nn_cell_size : density_edge(c);
+    // the same constellation was planned before (repeated passes over the same maps): one iteration at the remembered edge
+    PlanCache &pc = ctx->plan_cache[which];
+    bool hit = pc.valid && !getenv("ME_NO_PLAN_CACHE") && pc.n == c.n && pc.other_n == (other ? other->n : -1) && pc.v_req == v_req &&
+               pc.nn_cell == ctx->nn_cell_size && pc.budget == budget && pc.sp == sp && pc.slab_request == ctx->slab_request &&
+               pc.rank == ctx->rank && pc.world == ctx->world;
+    for (int a = 0; a < 3 && hit; ++a) {
+      hit = pc.bmin[a] == c.bbox_min[a] && pc.bmax[a] == c.bbox_max[a];
+      if (hit && other) hit = pc.obmin[a] == other->bbox_min[a] && pc.obmax[a] == other->bbox_max[a];
+    }
+    if (hit) h_target = pc.h_target;
     bool have = false;
+    double h_used = h_target;
     for (int iter = 0; iter < 4; ++iter) {
       Lattice cand;
       double v; int m;
@@ -840,16 +851,23 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
         double vs; int ms;
         if (pick_spec(c, other, v_req, h_target, budget, &vs, &ms, &cs, true)) { cand = cs; v = vs; m = ms; ok = true; }
       }
-      if (!ok)
+      if (!ok) {
+        if (have) break;      // the refined edge does not fit: keep the lattice of the previous iteration
         return fail(ctx, ME_ERR_RANGE, v_req > 0 ? "voxel size too small for the lattice (dense budget and sparse limits exceeded)"
                                                  : "cannot fit the cloud into the lattice");
+      }
       if (have && cand.sparse == L.sparse && cand.m == L.m && cand.v == L.v && cand.dims[0] == L.dims[0]) break;   // refinement changed nothing
       L = cand; have = true;
+      h_used = h_target;
       ctx->spec_v = v; ctx->spec_m = m;
       long long max_count = 0;
       if (L.sparse) { ME_TRY(build_sparse(ctx, c, L, &occupied)); built = true; }
       else { built = false; ME_TRY(histogram(ctx, c, L)); }
       if (ctx->nn_cell_size > 0) break;   // caller fixed the cell size
+      if (hit && L.sparse == pc.lat.sparse && L.m == pc.lat.m && L.v == pc.lat.v && L.dims[0] == pc.lat.dims[0] &&
+          L.dims[1] == pc.lat.dims[1] && L.dims[2] == pc.lat.dims[2])
+        break;                            // the remembered lattice: no need to measure the occupancy again
+      hit = false;
       if (!L.sparse) ME_TRY(occupancy(ctx, c, L, &occupied, &max_count));
       const double mean_occ = (double)c.n / (double)std::max<long long>(1, occupied);
       if (mean_occ <= 4.0 || iter == 3) break;
@@ -858,6 +876,20 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
       if (h_new >= 0.9 * L.h) break;
       h_target = h_new;
     }
+    if (hit && pc.slab_planned) {          // the slabs of this constellation
+      ctx->slab_planned = true; ctx->slab_on = pc.slab_on; ctx->slab_axis = pc.slab_axis;
+      ctx->slab_k0 = pc.slab_k0; ctx->slab_k1 = pc.slab_k1;
+    }
+    pc.valid = true;
+    pc.n = c.n; pc.other_n = other ? other->n : -1;
+    for (int a = 0; a < 3; ++a) {
+      pc.bmin[a] = c.bbox_min[a]; pc.bmax[a] = c.bbox_max[a];
+      pc.obmin[a] = other ? other->bbox_min[a] : 0.0; pc.obmax[a] = other ? other->bbox_max[a] : 0.0;
+    }
+    pc.v_req = v_req; pc.nn_cell = ctx->nn_cell_size; pc.budget = budget; pc.sp = sp; pc.slab_request = ctx->slab_request;
+    pc.rank = ctx->rank; pc.world = ctx->world;
+    pc.h_target = h_used; pc.lat = L;
+    pc.slab_planned = false;               // filled in below, once the slabs are planned on this lattice
   }
   c.grid_solo = solo;
   c.solo_h = solo ? solo_h : 0.0;
@@ -868,6 +900,14 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
   c.n_owned = c.n;
   if (!built && !solo && slab_wanted(ctx)) {
     if (!ctx->slab_planned) ME_TRY(plan_slabs(ctx, c, L));
+    {
+      PlanCache &pc = ctx->plan_cache[which];
+      if (pc.valid && !pc.slab_planned && pc.lat.dims[0] == L.dims[0] && pc.lat.dims[1] == L.dims[1] && pc.lat.dims[2] == L.dims[2] &&
+          pc.lat.m == L.m && pc.lat.v == L.v) {
+        pc.slab_planned = true; pc.slab_on = ctx->slab_on; pc.slab_axis = ctx->slab_axis;
+        pc.slab_k0 = ctx->slab_k0; pc.slab_k1 = ctx->slab_k1;
+      }
+    }
     if (ctx->slab_on) {
       slab_planes(ctx, L, c);
       unsigned long long *d_own = (unsigned long long *)ctx->d_scratch + 11;

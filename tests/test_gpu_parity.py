@@ -526,3 +526,31 @@ def test_device_resident_accumulators_equal_the_host_path(api, O):
     for a, b in ((m_e, m_e2), (m_g, m_g2)):
         assert (a.n_query, a.n_valid) == (b.n_query, b.n_valid)
         np.testing.assert_allclose([a.sum_entropy, a.min_entropy, a.max_entropy], [b.sum_entropy, b.min_entropy, b.max_entropy], rtol=1e-12)
+
+
+def test_repeated_passes_over_the_same_maps_reuse_the_lattice_plan(api, O, monkeypatch):
+    """The lattice plan (refined cell edge) of a cloud pair is remembered by the context: setting the same clouds again plans in
+    one step.  Results are those of a fresh context, with and without the memory (ME_NO_PLAN_CACHE)."""
+    est, gt, cfg = synth.make_pair("C2", scale=0.1)
+    p = A.make_nn_params(cfg["tau"], 1.0)
+    got = []
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("ME_NO_PLAN_CACHE", env)
+        with api.MapEvalB200(vmd_voxel_size=cfg["vmd_voxel_size"]) as ctx:
+            for rep in range(3):
+                ctx.set_cloud(A.ME_CLOUD_EST, est)
+                ctx.set_cloud(A.ME_CLOUD_GT, gt if rep != 1 else gt[: len(gt) // 2])      # pass 1: another pair in between
+                m = ctx.eval_mme_accum(A.ME_CLOUD_EST, cfg["nn_radius"], 10)
+                e, g = ctx.eval_nn_accum(p)
+                awd = ctx.calculateVMD(cfg["vmd_voxel_size"], 20, 5)
+                if rep != 1:
+                    got.append((A.struct_to_dict(e), A.struct_to_dict(g), (m.n_valid, m.sum_entropy), (awd.n_pairs, awd.awd, awd.scs)))
+    for other in got[1:]:
+        for a, b in zip(got[0][:2], other[:2]):
+            for k in ("n_query", "n_corr", "n_inlier", "n_ub"):
+                assert a[k] == b[k], k
+            for k in ("sum_d", "sum_d2", "sum_d_all", "sum_nn_dist"):
+                np.testing.assert_allclose(a[k], b[k], rtol=1e-12)
+        assert got[0][2][0] == other[2][0] and got[0][3][0] == other[3][0]
+        np.testing.assert_allclose([got[0][2][1], got[0][3][1], got[0][3][2]], [other[2][1], other[3][1], other[3][2]], rtol=1e-9)
