@@ -10,9 +10,9 @@ for spec in "$@"; do
   for attempt in 1 2; do
     PORT=$((PORT+1))
     if [ "$N" = "1" ]; then
-      timeout 240 python bench.py --gpus 1 --config $CFG --steps $STEPS --warmup 3 --no-cpu-baseline > gpurun_out/$tag.json 2> gpurun_out/$tag.err
+      timeout 150 python bench.py --gpus 1 --config $CFG --steps $STEPS --warmup 3 --no-cpu-baseline > gpurun_out/$tag.json 2> gpurun_out/$tag.err
     else
-      timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
+      timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
         bench.py --gpus $N --config $CFG --steps $STEPS --warmup 3 --no-cpu-baseline --layout $LAYOUT > gpurun_out/$tag.json 2> gpurun_out/$tag.err
     fi
     rc=$?
