@@ -9,9 +9,10 @@ estimated map (and of the GT map when the config says so), per-voxel Gaussians, 
   value : est points / step time with both clouds already resident in HBM (device-resident arm)
   e2e   : the same pass through the C-ABI with HOST (pinned) buffers: H2D of both clouds and D2H of the result
           structs are inside the timed region
-N > 1 (torchrun, one rank per GPU): the query ranges of the NN and MME sweeps are sharded by rank, both lattices are
-replicated, and the sum-reducible accumulators are all-reduced over NCCL once per step (strong scaling: the cloud
-pair is fixed).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+N > 1 (torchrun, one rank per GPU): slab layout — every rank lays out and evaluates only the voxel layers it owns of both
+clouds (lattice builds, sweeps and voxel stage sharded; `--layout replicated`: whole lattices on every rank, query ranges
+sharded; scenes that cannot be cut fall back to it), the W table of the voxel stage is MAX-all-reduced and the
+sum-reducible accumulators are all-reduced in place over NCCL once per step (strong scaling: the cloud pair is fixed).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on the SAME workload as the
 CUDA arm (C3 by default: 10 M vs 10 M); its timed passes are capped by wall time (REF_BUDGET_S) and the line says how
 many ran.  `e2e_pageable` repeats the e2e arm from plain (pageable) numpy memory, the way a std::vector caller hands

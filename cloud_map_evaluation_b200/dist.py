@@ -1,5 +1,7 @@
-"""Multi-GPU plumbing: one process per GPU, the evaluated cloud's query tiles/ranges sharded by rank, both lattices
-replicated, and ONE all-reduce of the sum-reducible accumulators (plus a MIN/MAX pair for the entropy extrema).
+"""Multi-GPU plumbing: one process per GPU; the evaluated cloud's query ranges sharded by rank with both lattices laid out whole
+(replicated layout), or every rank laying out and evaluating only its voxel layers (slab layout, MapEvalB200.set_layout); ONE
+all-reduce of the sum-reducible accumulators (plus a MAX pair for the entropy extrema; on a slab layout a MAX all-reduce of
+the voxel stage's W table).
 
 The reference is single-process; this is the B200-native equivalent of its TBB/OpenMP reductions
 (map_eval.cpp:1411,1420,1704-1708).  torch.distributed is used for the collectives only: backend "nccl" on GPUs

@@ -139,8 +139,8 @@ def _cmp_job(job, ref, n_est, n_gt, world):
             np.testing.assert_array_equal(idx[sel, cols], exp[0])
 
 
-# Small outdoor scenes would get the sparse cell table (laid out whole -> replicated layout); the full-size lattices that the
-# slab layout is for are dense.  A caller-fixed cell edge of 0.5 m keeps these scaled-down scenes on the dense table.
+# Surface scenes refine to cell edges whose dense table exceeds the budget and get the sparse cell table, which is laid out whole
+# (-> replicated layout).  A caller-fixed cell edge of 0.5 m keeps this scaled-down scene on the dense table.
 OUTDOOR = dict(nn_cell_size=0.5)
 
 
