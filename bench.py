@@ -102,12 +102,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+VOXEL_HASH_NOTE = ("voxel maps keyed with a mixing hash instead of the reference's XOR hash (voxel_calculator.hpp:18-22), whose "
+                   "collisions make the reference-faithful voxel stage of C3 take 444 s (tests/golden/c3_oracle.json, oracle_seconds): "
+                   "this baseline is FASTER than the reference's own code; same voxel Gaussians, AWD / SCS equal to 1e-15")
+
+
 def _cpu_pass(est, gt, cfg, threads, faithful=False):
     """One full pass with the oracle (the CPU restatement of the reference).  faithful=True keeps the reference's own
     threading: serial 1-NN loops on path A (map_eval.cpp:1215-1236), TBB / OpenMP for the estimated map's MME
-    (:1716-1717), serial MME of the ground truth (:1451); otherwise every sweep uses all `threads`."""
+    (:1716-1717), serial MME of the ground truth (:1451) — and its XOR voxel hash; otherwise every sweep uses all `threads`
+    and the voxel maps a mixing hash (VOXEL_HASH_NOTE)."""
     from oracle import oracle as O
     p = A.make_nn_params(cfg["tau"], 1.0)
+    O.set_voxel_hash(not faithful)
     t0 = time.perf_counter()
     O.eval_nn(est, gt, p, threads=1 if faithful else threads)
     if cfg["mme"]:
@@ -116,7 +123,9 @@ def _cpu_pass(est, gt, cfg, threads, faithful=False):
             O.eval_mme(gt, cfg["nn_radius"], 5, threads=1 if faithful else threads)
     if cfg["awd"]:
         O.eval_awd(est, gt, cfg["vmd_voxel_size"], 100, 5)
-    return time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    O.set_voxel_hash(False)
+    return dt
 
 
 def _host_threads():
@@ -135,13 +144,14 @@ def _cpu_sample(name, target_pts=1_000_000):
     return est, gt, cfg, scale
 
 
-REF_BUDGET_S = 200.0      # wall-time cap of the reference arm's timed passes (the driver allows minutes, not hours)
+REF_BUDGET_S = 150.0      # wall-time cap of the reference arm's timed passes (the driver allows minutes, not hours)
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port: Open3D/Eigen/TBB are absent) on the same
     config as the CUDA arm, at full size.  One pass over 10 M vs 10 M points takes the better part of a minute on 128
-    cores, so the number of timed passes is capped by wall time; `steps` is what actually ran."""
+    cores (with the voxel maps on a mixing hash — VOXEL_HASH_NOTE; 8 minutes with the reference's own hash), so the number of
+    timed passes is capped by wall time; `steps` is what actually ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,9 +166,8 @@ def run_reference(args):
             break
     dt = float(np.mean(times))
     v = len(est) / dt / 1e6
-    # SURVEY §8d mode (1), the reference's own threading (serial 1-NN loops, serial GT MME): on a 1 M-point sample only —
-    # at full size the serial loops alone take minutes.  (At C3 one full-size pass already takes ~8 min on 128 cores, 7 of
-    # them in the serial voxel-map build whose XOR hash — voxel_calculator.hpp:18-22, restated faithfully — collides.)
+    # SURVEY §8d mode (1), the reference's own threading (serial 1-NN loops, serial GT MME) and voxel hash: on a 1 M-point
+    # sample only — at full size the serial loops alone take minutes and the voxel-map build 7 more.
     s_est, s_gt, s_cfg, s_scale = _cpu_sample(args.config)
     dt_f = _cpu_pass(s_est, s_gt, s_cfg, threads, faithful=True)
     sample = (f"{args.config} at full size ({len(est)} est vs {len(gt)} gt points), full pass, all-cores mode, "
@@ -171,9 +180,11 @@ def run_reference(args):
         "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "n_est": len(est), "n_gt": len(gt),
                    "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "pass_seconds": times,
+                         "pass_seconds": times, "voxel_hash": VOXEL_HASH_NOTE,
+                         "reference_faithful_pass_seconds_c3": "485 (NN 18 + MME 23 + voxel stage 444; B200 host, 128 threads, "
+                                                               "tests/golden/c3_oracle.json)",
                          "reference_threading_value": len(s_est) / dt_f / 1e6,
-                         "reference_threading": f"serial 1-NN loops and GT MME as the reference runs them, est MME on all cores; "
+                         "reference_threading": f"serial 1-NN loops and GT MME as the reference runs them, est MME on all cores, XOR voxel hash; "
                                                 f"{args.config} at scale {s_scale:g} ({len(s_est)} points)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -407,7 +418,7 @@ def main():
             threads = _host_threads()
             s_est, s_gt, s_cfg, s_scale = _cpu_sample(args.config)
             dt = _cpu_pass(s_est, s_gt, s_cfg, threads)
-            cpu = {"value": len(s_est) / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            cpu = {"value": len(s_est) / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "voxel_hash": VOXEL_HASH_NOTE,
                    "sample": f"{args.config} at scale {s_scale:g} ({len(s_est)} est vs {len(s_gt)} gt points, same "
                              f"density), one full pass in {dt:.1f} s, all-cores mode"}
         nn = results["nn"]

@@ -39,6 +39,8 @@ def lib():
         L.oracle_eval_awd.argtypes = [dp, C.c_int64, dp, C.c_int64, C.c_double, C.c_int32, C.c_int32,
                                       C.POINTER(A.me_awd_result), C.POINTER(C.c_int64), C.POINTER(dp)]
         L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_set_voxel_hash.argtypes = [C.c_int]
+        L.oracle_set_voxel_hash.restype = None
         L.oracle_wasserstein.restype = C.c_double
         L.oracle_wasserstein.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int]
         L.oracle_scs.argtypes = [ip, dp, C.c_int64, C.c_int, dp, C.POINTER(C.c_int64)]
@@ -129,6 +131,12 @@ def eval_awd(est, gt, voxel_size, min_points=100, scs_radius=5, want_rows=False)
         else np.zeros((0, 27))
     lib().oracle_free(rows_p)
     return res, rows
+
+
+def set_voxel_hash(fast):
+    """False (default): the reference's XOR voxel hash; True: a mixing hash — same voxel Gaussians, another iteration
+    order, ~100x faster on large clouds.  Used by bench.py's timed CPU baseline only."""
+    lib().oracle_set_voxel_hash(1 if fast else 0)
 
 
 def wasserstein(mu1, sigma1, n1, mu2, sigma2, n2):

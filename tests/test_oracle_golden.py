@@ -63,3 +63,21 @@ def test_awd_and_scs_known_answers(golden_dir):
     scs, count = O.scs(keys, w, radius=5)
     assert abs(scs - log["SCS"]) <= 4 * half_ulp, scs
     assert count == len(w) - 1  # one voxel has no neighbour inside the 11^3 window
+
+
+def test_voxel_hash_mode_changes_speed_not_results():
+    """bench.py times the CPU baseline with a mixing voxel hash (the reference's XOR hash makes its voxel maps degenerate):
+    counts identical, AWD / SCS equal to summation order."""
+    from oracle import oracle as O
+    from cloud_map_evaluation_b200 import synth
+    est, gt, cfg = synth.make_pair("C2", scale=0.1)
+    a = O.eval_awd(est, gt, cfg["vmd_voxel_size"], 20, 5)
+    O.set_voxel_hash(True)
+    try:
+        b = O.eval_awd(est, gt, cfg["vmd_voxel_size"], 20, 5)
+    finally:
+        O.set_voxel_hash(False)
+    for k in ("n_pairs", "n_scs", "n_voxels_est", "n_voxels_gt", "n_active", "n_old", "n_new"):
+        assert getattr(a, k) == getattr(b, k), k
+    assert a.n_pairs > 10
+    np.testing.assert_allclose([a.awd, a.scs], [b.awd, b.scs], rtol=1e-12)
