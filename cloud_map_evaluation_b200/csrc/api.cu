@@ -282,6 +282,24 @@ int me_set_layout(me_ctx *ctx, int32_t layout) {
   return ME_OK;
 }
 
+int me_plan_slab_cut(const uint64_t *plane_counts_y, int32_t n_planes_y, const uint64_t *plane_counts_z, int32_t n_planes_z,
+                     int32_t cells_per_voxel, int32_t world, int32_t halo_cells, int32_t *axis, int32_t *layer_bounds,
+                     double *busiest_share) {
+  if (!plane_counts_y || !plane_counts_z || !axis || !layer_bounds || !busiest_share) return ME_ERR_INVALID;
+  if (n_planes_y < 0 || n_planes_z < 0 || cells_per_voxel < 1 || world < 1 || halo_cells < 0) return ME_ERR_INVALID;
+  static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "plane counts are 64-bit");
+  int ax = 0;
+  double share = 2.0;
+  std::vector<int> b((size_t)world + 1, 0);
+  me::slab_cut((const unsigned long long *)plane_counts_y, n_planes_y, (const unsigned long long *)plane_counts_z, n_planes_z,
+               cells_per_voxel, world, halo_cells, &ax, b.data(), &share);
+  if (ax && share > me::kSlabMaxShare) ax = 0;
+  *axis = ax;
+  *busiest_share = share;
+  for (int r = 0; r <= world; ++r) layer_bounds[r] = ax ? b[r] : 0;
+  return ME_OK;
+}
+
 int me_layout_active(me_ctx *ctx, int32_t *layout, int32_t *axis, int64_t n_laid_out[2], int64_t n_owned[2]) {
   ME_ENTER(ctx);
   const bool slab = (ctx->cloud[0].grid_valid && ctx->cloud[0].slab) || (ctx->cloud[1].grid_valid && ctx->cloud[1].slab);

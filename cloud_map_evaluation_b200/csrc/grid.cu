@@ -713,6 +713,48 @@ __global__ void __launch_bounds__(kThreads) slab_mask_kernel(uint32_t *__restric
 
 static bool slab_wanted(const me_ctx *ctx) { return ctx->slab_request && ctx->world > 1 && getenv("ME_NO_SLAB") == nullptr; }
 
+// The cut itself — pure host arithmetic on the per-plane point counts along y and z (also behind me_plan_slab_cut for the CPU
+// tests).  The voxel layers of an axis (m planes each) are cut into `world` contiguous groups of about equal point count;
+// the axis whose busiest rank lays out (owned layers + halo planes) the smallest share of the cloud wins.  *axis = 0 if
+// neither axis has 2 * world layers.  bounds[0..world]: first owned layer of every rank (bounds[world] = number of layers).
+void slab_cut(const unsigned long long *planes_y, int n_planes_y, const unsigned long long *planes_z, int n_planes_z, int m,
+              int world, int halo, int *axis_out, int *bounds, double *share_out) {
+  const int W = world, H = halo;
+  double best_share = 2.0;
+  std::vector<int> best_b;
+  int best_axis = 0;
+  for (int axis = 1; axis <= 2; ++axis) {
+    const unsigned long long *hp = axis == 2 ? planes_z : planes_y;
+    const int nl = (axis == 2 ? n_planes_z : n_planes_y) / std::max(1, m);
+    if (nl < 2 * W) continue;                            // too few voxel layers to cut
+    std::vector<unsigned long long> cum((size_t)nl * m + 1, 0);      // per plane
+    for (int p = 0; p < nl * m; ++p) cum[p + 1] = cum[p] + hp[p];
+    const unsigned long long total = cum[(size_t)nl * m];
+    if (total == 0) continue;
+    std::vector<int> b((size_t)W + 1, 0);
+    b[W] = nl;
+    for (int r = 1; r < W; ++r) {
+      const unsigned long long want = total / (unsigned long long)W * (unsigned long long)r;
+      int lo = b[r - 1] + 1, hi = nl - (W - r);
+      int l = lo;
+      while (l < hi && cum[(size_t)l * m] < want) ++l;      // first layer boundary at or past the target
+      if (l > lo && want - cum[(size_t)(l - 1) * m] < cum[(size_t)l * m] - want) --l;
+      b[r] = l;
+    }
+    // the share of the cloud the busiest rank lays out (owned layers + halo)
+    unsigned long long worst = 0;
+    for (int r = 0; r < W; ++r) {
+      const int p0 = std::max(0, b[r] * m - H), p1 = std::min(nl * m, b[r + 1] * m + H);
+      worst = std::max(worst, cum[p1] - cum[p0]);
+    }
+    const double share = (double)worst / (double)total;
+    if (share < best_share) { best_share = share; best_b = b; best_axis = axis; }
+  }
+  *axis_out = best_axis;
+  *share_out = best_share;
+  if (best_axis) for (int r = 0; r <= W; ++r) bounds[r] = best_b[r];
+}
+
 // plan the owned voxel layers of every rank from the layer histograms of cloud c (histogram in c.d_cell_off + 1); the same
 // arithmetic on the same (replicated) cloud on every rank gives the same plan
 static int plan_slabs(me_ctx *ctx, Cloud &c, const Lattice &L) {
@@ -729,41 +771,15 @@ static int plan_slabs(me_ctx *ctx, Cloud &c, const Lattice &L) {
   std::vector<unsigned long long> h((size_t)np);
   ME_CUDA(ctx, cudaMemcpyAsync(h.data(), d_pl, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   ME_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  double best_share = 2.0;
-  std::vector<int> best_b;
   int best_axis = 0;
-  for (int axis = 1; axis <= 2; ++axis) {
-    const int nl = L.nvox[axis];
-    if (nl < 2 * W) continue;                            // too few voxel layers to cut
-    const unsigned long long *hp = h.data() + (axis == 2 ? L.dims[1] : 0);
-    std::vector<unsigned long long> cum((size_t)nl * L.m + 1, 0);      // per plane
-    for (int p = 0; p < nl * L.m; ++p) cum[p + 1] = cum[p] + hp[p];
-    const unsigned long long total = cum[(size_t)nl * L.m];
-    if (total == 0) continue;
-    std::vector<int> b((size_t)W + 1, 0);
-    b[W] = nl;
-    for (int r = 1; r < W; ++r) {
-      const unsigned long long want = total / (unsigned long long)W * (unsigned long long)r;
-      int lo = b[r - 1] + 1, hi = nl - (W - r);
-      int l = lo;
-      while (l < hi && cum[(size_t)l * L.m] < want) ++l;      // first layer boundary at or past the target
-      if (l > lo && want - cum[(size_t)(l - 1) * L.m] < cum[(size_t)l * L.m] - want) --l;
-      b[r] = l;
-    }
-    // the share of the cloud the busiest rank lays out (owned layers + halo)
-    unsigned long long worst = 0;
-    for (int r = 0; r < W; ++r) {
-      const int p0 = std::max(0, b[r] * L.m - H), p1 = std::min(nl * L.m, b[r + 1] * L.m + H);
-      worst = std::max(worst, cum[p1] - cum[p0]);
-    }
-    const double share = (double)worst / (double)total;
-    if (share < best_share) { best_share = share; best_b = b; best_axis = axis; }
-  }
+  double best_share = 2.0;
+  std::vector<int> best_b((size_t)W + 1, 0);
+  slab_cut(h.data(), L.dims[1], h.data() + L.dims[1], L.dims[2], L.m, W, H, &best_axis, best_b.data(), &best_share);
   if (getenv("ME_DEBUG_SLAB"))
     fprintf(stderr, "[mapeval] slab plan: rank %d/%d lattice %d x %d x %d (m = %d), axis %d, busiest share %.3f\n", ctx->rank, W,
             L.dims[0], L.dims[1], L.dims[2], L.m, best_axis, best_share);
   // worth it only if the busiest rank lays out clearly less than the whole cloud
-  if (best_axis == 0 || best_share > 0.75) return ME_OK;
+  if (best_axis == 0 || best_share > kSlabMaxShare) return ME_OK;
   const int r = ctx->rank;
   ctx->slab_axis = best_axis;
   ctx->slab_k0 = r == 0 ? LLONG_MIN / 4 : (long long)L.k_lo[best_axis] + best_b[r];

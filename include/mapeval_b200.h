@@ -177,6 +177,15 @@ ME_API int  me_set_layout(me_ctx *ctx, int32_t layout);
 /* after the lattices were built (any sweep): *layout = the layout in force, *axis = 1 (y) / 2 (z) / 0, n_laid_out[2] = the
  * points of (est, gt) this rank laid out, n_owned[2] = the points it evaluates.  Any pointer may be NULL. */
 ME_API int  me_layout_active(me_ctx *ctx, int32_t *layout, int32_t *axis, int64_t n_laid_out[2], int64_t n_owned[2]);
+/* The planner of the slab layout as a pure host function (no context, no device): given the number of points in every
+ * lattice plane along y and along z (cells_per_voxel planes per voxel layer), cut the voxel layers of one axis into `world`
+ * contiguous groups of about equal point count.  *axis = 1 (y) / 2 (z), or 0 when the scene cannot be cut (fewer than
+ * 2 x world layers on both axes, or the busiest rank — owned layers + halo_cells planes either side — would lay out more than
+ * 75 % of the points); layer_bounds[0..world] = first owned layer of every rank; *busiest_share = that rank's share.  This
+ * is the arithmetic every rank runs on the (replicated) cloud's histogram, which is why the ranks agree without talking. */
+ME_API int  me_plan_slab_cut(const uint64_t *plane_counts_y, int32_t n_planes_y, const uint64_t *plane_counts_z,
+                             int32_t n_planes_z, int32_t cells_per_voxel, int32_t world, int32_t halo_cells, int32_t *axis,
+                             int32_t *layer_bounds, double *busiest_share);
 ME_API int  me_synchronize(me_ctx *ctx);
 
 /* replaces: io::ReadPointCloud* results held in map_3d_/gt_3d_ (map_eval.cpp:10-21) — the clouds the path reads.
