@@ -20,6 +20,11 @@ ME_CUTOFF_DIST_LT_R = 1
 ME_PAIRING_AS_WRITTEN = 0
 ME_PAIRING_GEOMETRIC = 1
 
+class me_lattice_plan(C.Structure):
+    _fields_ = [("v", C.c_double), ("h", C.c_double), ("m", C.c_int32), ("sparse", C.c_int32), ("nvox", C.c_int32 * 3),
+                ("dims", C.c_int32 * 3), ("ncells", C.c_int64)]
+
+
 ME_LAYOUT_REPLICATED = 0
 ME_LAYOUT_SLAB = 1
 ME_ICP_POINT_TO_POINT = 0

@@ -20,7 +20,7 @@ SYMBOLS = (
     "me_eval_awd", "me_awd_from_rows", "me_free", "me_get_stage_times", "me_launch_count",
     "me_accum_reset", "me_eval_nn_accum_device", "me_eval_mme_accum_device", "me_accum_block", "me_accum_fetch",
     "me_set_layout", "me_layout_active", "me_voxel_begin", "me_voxel_w_table", "me_voxel_finish_accum_device", "me_accum_fetch_awd",
-    "me_plan_slab_cut",
+    "me_plan_slab_cut", "me_plan_lattice",
 )
 
 _lib = None
@@ -81,6 +81,8 @@ def load():
                                  C.POINTER(A.me_mme_accum)]
     L.me_set_layout.argtypes = [ctx, C.c_int32]
     L.me_layout_active.argtypes = [ctx, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.me_plan_lattice.argtypes = [dp, dp, C.c_int64, dp, dp, C.c_int64, C.c_double, C.c_double, C.c_int64, C.c_int32,
+                                  C.POINTER(A.me_lattice_plan)]
     L.me_plan_slab_cut.argtypes = [C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.me_voxel_begin.argtypes = [ctx, C.c_double, C.c_int32]

@@ -282,6 +282,22 @@ int me_set_layout(me_ctx *ctx, int32_t layout) {
   return ME_OK;
 }
 
+int me_plan_lattice(const double bbox_min[3], const double bbox_max[3], int64_t n, const double *other_bbox_min,
+                    const double *other_bbox_max, int64_t other_n, double voxel_size, double cell_edge_target,
+                    int64_t max_grid_cells, int32_t allow_sparse, me_lattice_plan *out) {
+  if (!bbox_min || !bbox_max || !out || n < 1) return ME_ERR_INVALID;
+  for (int a = 0; a < 3; ++a)
+    if (!(bbox_min[a] <= bbox_max[a])) return ME_ERR_INVALID;
+  me::Lattice L;
+  if (!me::plan_lattice_host(bbox_min, bbox_max, n, other_bbox_min, other_bbox_max, other_n, voxel_size, cell_edge_target,
+                             max_grid_cells, allow_sparse != 0, &L))
+    return ME_ERR_RANGE;
+  out->v = L.v; out->h = L.h; out->m = L.m; out->sparse = L.sparse;
+  for (int a = 0; a < 3; ++a) { out->nvox[a] = L.nvox[a]; out->dims[a] = L.dims[a]; }
+  out->ncells = L.sparse ? 0 : L.ncells;
+  return ME_OK;
+}
+
 int me_plan_slab_cut(const uint64_t *plane_counts_y, int32_t n_planes_y, const uint64_t *plane_counts_z, int32_t n_planes_z,
                      int32_t cells_per_voxel, int32_t world, int32_t halo_cells, int32_t *axis, int32_t *layer_bounds,
                      double *busiest_share) {

@@ -294,6 +294,8 @@ static constexpr int kBlkTotal = kBlkSumCount + kBlkMaxCount;
 int unsort_entropy(me_ctx *ctx, int which, double *h_entropy);
 int run_awd(me_ctx *ctx, double voxel_size, int min_points, int scs_radius, me_awd_result *out, int64_t *n_rows,
             double **rows27);
+bool plan_lattice_host(const double bmin[3], const double bmax[3], long long n, const double *obmin, const double *obmax,
+                       long long other_n, double v_req, double h_target, long long budget, bool allow_sparse, Lattice *out);
 static constexpr double kSlabMaxShare = 0.75;      // a slab cut whose busiest rank lays out more than this share is not worth it
 void slab_cut(const unsigned long long *planes_y, int n_planes_y, const unsigned long long *planes_z, int n_planes_z, int m,
               int world, int halo, int *axis_out, int *bounds, double *share_out);

@@ -464,6 +464,37 @@ static bool pick_spec(const Cloud &c, const Cloud *other, double v_req, double h
   return false;
 }
 
+// one planning step: the dense table at the wanted edge if it fits the budget; if the budget forces cells noticeably coarser
+// than wanted (or nothing fits), a sparse table at the wanted edge instead
+static bool choose_lattice(const Cloud &c, const Cloud *other, double v_req, double h_target, long long budget, bool sp,
+                           double *v, int *m, Lattice *cand) {
+  bool ok = pick_spec(c, other, v_req, h_target, budget, v, m, cand, false);
+  if (sp && (!ok || cand->h > 1.25 * h_target)) {
+    Lattice cs;
+    double vs; int ms;
+    if (pick_spec(c, other, v_req, h_target, budget, &vs, &ms, &cs, true)) { *cand = cs; *v = vs; *m = ms; ok = true; }
+  }
+  return ok;
+}
+
+static long long auto_budget(long long n_max) { return std::min<long long>(1ll << 31, std::max<long long>(1ll << 28, 16 * n_max)); }
+
+// the planning step as a pure host function (me_plan_lattice): bounding boxes and sizes in, lattice out
+bool plan_lattice_host(const double bmin[3], const double bmax[3], long long n, const double *obmin, const double *obmax,
+                       long long other_n, double v_req, double h_target, long long budget, bool allow_sparse, Lattice *out) {
+  Cloud c, o;
+  c.n = n; o.n = other_n;
+  for (int a = 0; a < 3; ++a) {
+    c.bbox_min[a] = bmin[a]; c.bbox_max[a] = bmax[a];
+    o.bbox_min[a] = obmin ? obmin[a] : 0.0; o.bbox_max[a] = obmax ? obmax[a] : 0.0;
+  }
+  c.bbox_valid = true; o.bbox_valid = obmin && obmax;
+  if (budget <= 0) budget = auto_budget(std::max(n, o.bbox_valid ? other_n : 0));
+  if (!(h_target > 0)) h_target = density_edge(c);
+  double v; int m;
+  return choose_lattice(c, o.bbox_valid ? &o : nullptr, v_req, h_target, budget, allow_sparse, &v, &m, out);
+}
+
 // in-place exclusive scan of n uint32 (3 phases; the per-tile partials live in a small buffer of their own, so callers
 // may keep data in the work buffer across the scan)
 int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
@@ -485,8 +516,7 @@ int exclusive_scan_inplace(me_ctx *ctx, uint32_t *a, long long n) {
 static long long grid_budget(const me_ctx *ctx) {
   if (getenv("ME_FORCE_SPARSE")) return 1;      // test hook: every lattice gets a sparse cell table
   if (ctx->max_grid_cells > 0) return ctx->max_grid_cells;
-  const long long n = std::max(ctx->cloud[0].n, ctx->cloud[1].n);
-  return std::min<long long>(1ll << 31, std::max<long long>(1ll << 28, 16 * n));
+  return auto_budget(std::max(ctx->cloud[0].n, ctx->cloud[1].n));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -860,13 +890,7 @@ int build_grid(me_ctx *ctx, int which, double solo_h) {
     for (int iter = 0; iter < 4; ++iter) {
       Lattice cand;
       double v; int m;
-      // dense first; if the budget forces cells noticeably coarser than wanted, a sparse table at the wanted edge instead
-      bool ok = pick_spec(c, other, v_req, h_target, budget, &v, &m, &cand, false);
-      if (sp && (!ok || cand.h > 1.25 * h_target)) {
-        Lattice cs;
-        double vs; int ms;
-        if (pick_spec(c, other, v_req, h_target, budget, &vs, &ms, &cs, true)) { cand = cs; v = vs; m = ms; ok = true; }
-      }
+      const bool ok = choose_lattice(c, other, v_req, h_target, budget, sp, &v, &m, &cand);
       if (!ok) {
         if (have) break;      // the refined edge does not fit: keep the lattice of the previous iteration
         return fail(ctx, ME_ERR_RANGE, v_req > 0 ? "voxel size too small for the lattice (dense budget and sparse limits exceeded)"

@@ -154,6 +154,16 @@ typedef struct {             /* == open3d RegistrationResult (map_eval.cpp:1367-
   int32_t iterations, converged;     /* updates applied; 1 if the relative criteria stopped the loop             */
 } me_icp_result;
 
+/* one planning step of the cell lattice (me_plan_lattice) */
+typedef struct {
+  double  v, h;            /* voxel edge; cell edge h = v / m                                  */
+  int32_t m;               /* cells per voxel edge                                             */
+  int32_t sparse;          /* 1: occupied 32-cell row segments + hash; 0: dense table          */
+  int32_t nvox[3];         /* voxels per axis                                                  */
+  int32_t dims[3];         /* cells per axis = nvox * m                                        */
+  int64_t ncells;          /* dense table: cells (4 B each); sparse: 0                         */
+} me_lattice_plan;
+
 /* ---- lifecycle ---------------------------------------------------------------------------------- */
 
 ME_API int  me_abi_version(void);
@@ -183,6 +193,15 @@ ME_API int  me_layout_active(me_ctx *ctx, int32_t *layout, int32_t *axis, int64_
  * 2 x world layers on both axes, or the busiest rank — owned layers + halo_cells planes either side — would lay out more than
  * 75 % of the points); layer_bounds[0..world] = first owned layer of every rank; *busiest_share = that rank's share.  This
  * is the arithmetic every rank runs on the (replicated) cloud's histogram, which is why the ranks agree without talking. */
+/* One planning step of the cell lattice as a pure host function (no context, no device): the lattice a cloud of n points
+ * with this bounding box gets for a wanted cell edge (<= 0: ~2 points per cell of the box volume), aligned with voxel_size
+ * (<= 0: free), fitting `other` (nullable bounding box of the second cloud) under the same spec, within max_grid_cells
+ * (<= 0: the automatic budget, 2^28 .. 2^31 growing with the clouds).  Dense if the dense table at that edge fits; sparse
+ * when the budget would force cells > 1.25x coarser (allow_sparse).  ME_ERR_RANGE if nothing fits.  The library runs this
+ * step 1-3 times per cloud pair, refining the edge on the measured occupancy in between. */
+ME_API int  me_plan_lattice(const double bbox_min[3], const double bbox_max[3], int64_t n, const double *other_bbox_min,
+                            const double *other_bbox_max, int64_t other_n, double voxel_size, double cell_edge_target,
+                            int64_t max_grid_cells, int32_t allow_sparse, me_lattice_plan *out);
 ME_API int  me_plan_slab_cut(const uint64_t *plane_counts_y, int32_t n_planes_y, const uint64_t *plane_counts_z,
                              int32_t n_planes_z, int32_t cells_per_voxel, int32_t world, int32_t halo_cells, int32_t *axis,
                              int32_t *layer_bounds, double *busiest_share);
