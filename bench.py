@@ -178,6 +178,8 @@ def run_reference(args):
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.config}: {synth.CONFIGS[args.config]['desc']}", "n_est": len(est), "n_gt": len(gt),
+                   "tau": cfg["tau"], "icp_max_distance": 1.0, "nn_radius": cfg["nn_radius"],
+                   "vmd_voxel_size": cfg["vmd_voxel_size"], "mme_gt": bool(cfg["gt_mme"]), "generated": "numpy",
                    "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "pass_seconds": times, "voxel_hash": VOXEL_HASH_NOTE,
